@@ -1,0 +1,265 @@
+// extern "C" entry points declared in include/demovlp_b200.h: validation + dispatch.
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dvlp {
+
+thread_local int g_last_cuda_error = 0;
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_default_impl{DVLP_IMPL_AUTO};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int run_prep(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, bool, char*,
+             const Workspace&, cudaStream_t);
+int run_pair_generic(bool backward, const PairArgs& a, int n_cta, cudaStream_t st);
+int run_grad_finalize(const void*, int, const float*, const float*, const float*, int, int, int, int, float*,
+                      cudaStream_t);
+int run_rwa_loss(const float*, int, int, int, int, float, float*, float*, cudaStream_t);
+int run_normsoftmax(const float*, int, int, float, float*, float*, float*, cudaStream_t);
+int run_sim_fwd(const void*, const void*, int, int, int, float, int, float*, float*, cudaStream_t);
+int run_sim_bwd(const void*, const void*, int, int, int, float, int, const float*, float*, float*, float*,
+                cudaStream_t);
+int run_ranks_t2v(const double*, int, int, int32_t*, cudaStream_t);
+int run_ranks_v2t(const double*, int, int, double*, cudaStream_t);
+// tcgen05 path (pair_tc.cu)
+bool tc_supported(int R, int W, int d);
+int run_pair_tc_fwd(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
+                    int focal, float* scores, char* ws, const Workspace& L, cudaStream_t st);
+int run_pair_tc_bwd(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
+                    int focal, const float* d_scores, char* ws, const Workspace& L, cudaStream_t st);
+bool tc_bwd_available();
+
+Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc) {
+  Workspace L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  const size_t nv = (size_t)Bv * R, nt = (size_t)Bt * W;
+  L.alpha = take(nv * 4);
+  L.beta = take(nt * 4);
+  L.mterm_v = take(nv * 4);
+  L.mterm_t = take(nt * 4);
+  if (tc) {
+    bool copy = in_dtype == DVLP_F32;
+    L.vh = take(copy ? nv * d * 2 : 0);
+    L.th = take(copy ? nt * d * 2 : 0);
+    L.gv = take(nv * R * 2);
+    L.gt = take(nt * W * 2);
+  } else {
+    L.vh = take(nv * d * 4);
+    L.th = take(nt * d * 4);
+    L.gv = take(nv * R * 4);
+    L.gt = take(nt * W * 4);
+  }
+  L.dvh = take(nv * d * 4);
+  L.dth = take(nt * d * 4);
+  L.dgv = take(nv * R * 4);
+  L.dgt = take(nt * W * 4);
+  // generic kernels (also the backward fallback of the tcgen05 forward): per-CTA scratch
+  long long pairs = (long long)Bv * Bt;
+  int sms = 148;
+  L.n_cta = (int)(pairs < (long long)sms * 4 ? pairs : (long long)sms * 4);
+  int Lmax = R > W ? R : W;
+  L.scratch_per_cta = align_up(((size_t)4 * R * W + 5 * Lmax) * 4) / 4;
+  L.scratch = take((size_t)L.n_cta * L.scratch_per_cta * 4);
+  L.total = off;
+  return L;
+}
+
+static int check_common(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
+                        int R, int W, int d, int in_dtype) {
+  if (!im || !s || !im_mask || !s_mask) return DVLP_ERR_NULL_POINTER;
+  if (Bv <= 0 || Bt <= 0 || R <= 0 || W <= 0 || d <= 0 || (d % 8) != 0) return DVLP_ERR_BAD_SHAPE;
+  if (in_dtype != DVLP_F32 && in_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
+  if (((uintptr_t)im | (uintptr_t)s) & 15) return DVLP_ERR_MISALIGNED;
+  return DVLP_OK;
+}
+
+static int pick_tc(int impl, int R, int W, int d, bool* tc) {
+  if (impl == DVLP_IMPL_AUTO) impl = g_default_impl.load();
+  if (impl == DVLP_IMPL_GENERIC) { *tc = false; return DVLP_OK; }
+  bool ok = tc_supported(R, W, d);
+  if (impl == DVLP_IMPL_TCGEN05 && !ok) return DVLP_ERR_BAD_SHAPE;
+  if (impl != DVLP_IMPL_AUTO && impl != DVLP_IMPL_TCGEN05) return DVLP_ERR_BAD_ARG;
+  *tc = ok;
+  return DVLP_OK;
+}
+
+static int device_ok() {
+  static int cached = 1;   // 1 = unknown
+  if (cached != 1) return cached;
+  int dev = 0;
+  cudaDeviceProp p;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+    return cached = DVLP_ERR_NO_DEVICE;
+  }
+  cached = (p.major == 10) ? DVLP_OK : DVLP_ERR_NO_DEVICE;
+  return cached;
+}
+
+}  // namespace dvlp
+
+using namespace dvlp;
+
+extern "C" {
+
+int dvlp_version(void) { return 100; }
+
+const char* dvlp_error_string(int code) {
+  switch (code) {
+    case DVLP_OK: return "ok";
+    case DVLP_ERR_BAD_SHAPE: return "bad or unsupported shape";
+    case DVLP_ERR_BAD_DTYPE: return "unsupported dtype";
+    case DVLP_ERR_NULL_POINTER: return "null pointer";
+    case DVLP_ERR_MISALIGNED: return "pointer not 16-byte aligned";
+    case DVLP_ERR_WORKSPACE: return "workspace missing or too small";
+    case DVLP_ERR_CUDA: return "CUDA error";
+    case DVLP_ERR_NO_DEVICE: return "no sm_100 CUDA device (no CPU fallback exists)";
+    case DVLP_ERR_BAD_ARG: return "bad argument";
+  }
+  return "unknown error";
+}
+
+int dvlp_last_cuda_error(void) { return g_last_cuda_error; }
+int dvlp_rw_tcgen05_supported(int R, int W, int d) { return tc_supported(R, W, d) ? 1 : 0; }
+void dvlp_set_default_impl(int impl) { g_default_impl.store(impl); }
+uint64_t dvlp_launch_count(void) { return g_launches.load(); }
+
+size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl) {
+  if (Bv <= 0 || Bt <= 0 || R <= 0 || W <= 0 || d <= 0) return 0;
+  bool tc = false;
+  if (pick_tc(impl, R, W, d, &tc) != DVLP_OK) return 0;
+  return make_workspace(Bv, Bt, R, W, d, in_dtype, tc).total;
+}
+
+int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
+                       int R, int W, int d, float lambda, int focal_equal, int in_dtype, int impl, float* scores,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(im, s, im_mask, s_mask, Bv, Bt, R, W, d, in_dtype);
+  if (rc) return rc;
+  if (!scores) return DVLP_ERR_NULL_POINTER;
+  bool tc = false;
+  if ((rc = pick_tc(impl, R, W, d, &tc))) return rc;
+  if ((rc = device_ok())) return rc;
+  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc);
+  if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
+  if ((uintptr_t)workspace & 255) return DVLP_ERR_MISALIGNED;
+  char* ws = (char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, ws, L, st))) return rc;
+  if (tc) {
+    const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vh);
+    const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.th);
+    return run_pair_tc_fwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, st);
+  }
+  PairArgs a{};
+  a.vh = (const float*)(ws + L.vh); a.th = (const float*)(ws + L.th);
+  a.gv = (const float*)(ws + L.gv); a.gt = (const float*)(ws + L.gt);
+  a.mterm_v = (const float*)(ws + L.mterm_v); a.mterm_t = (const float*)(ws + L.mterm_t);
+  a.Bv = Bv; a.Bt = Bt; a.R = R; a.W = W; a.d = d; a.lambda = lambda; a.focal = focal_equal;
+  a.scores = scores;
+  a.scratch = (float*)(ws + L.scratch); a.scratch_per_cta = L.scratch_per_cta;
+  return run_pair_generic(false, a, L.n_cta, st);
+}
+
+int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
+                       int R, int W, int d, float lambda, int focal_equal, int in_dtype, int impl,
+                       const float* d_scores, float* d_im, float* d_s, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  int rc = check_common(im, s, im_mask, s_mask, Bv, Bt, R, W, d, in_dtype);
+  if (rc) return rc;
+  if (!d_scores || !d_im || !d_s) return DVLP_ERR_NULL_POINTER;
+  bool tc = false;
+  if ((rc = pick_tc(impl, R, W, d, &tc))) return rc;
+  if ((rc = device_ok())) return rc;
+  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc);
+  if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  // zero the accumulators (one contiguous range: dvh .. dgt)
+  DVLP_CUDA_OK(cudaMemsetAsync(ws + L.dvh, 0, L.scratch - L.dvh, st));
+  int prescaled = 0;
+  if (tc) {
+    const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vh);
+    const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.th);
+    if ((rc = run_pair_tc_bwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, d_scores, ws, L, st))) return rc;
+    prescaled = 1;
+  } else {
+    PairArgs a{};
+    a.vh = (const float*)(ws + L.vh); a.th = (const float*)(ws + L.th);
+    a.gv = (const float*)(ws + L.gv); a.gt = (const float*)(ws + L.gt);
+    a.mterm_v = (const float*)(ws + L.mterm_v); a.mterm_t = (const float*)(ws + L.mterm_t);
+    a.Bv = Bv; a.Bt = Bt; a.R = R; a.W = W; a.d = d; a.lambda = lambda; a.focal = focal_equal;
+    a.d_scores = d_scores;
+    a.dvh = (float*)(ws + L.dvh); a.dth = (float*)(ws + L.dth);
+    a.dgv = (float*)(ws + L.dgv); a.dgt = (float*)(ws + L.dgt);
+    a.scratch = (float*)(ws + L.scratch); a.scratch_per_cta = L.scratch_per_cta;
+    if ((rc = run_pair_generic(true, a, L.n_cta, st))) return rc;
+  }
+  const void* xv = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.vh) : im;
+  const void* xt = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.th) : s;
+  int xdt = (tc && in_dtype == DVLP_F32) ? DVLP_BF16 : in_dtype;
+  if ((rc = run_grad_finalize(xv, xdt, (const float*)(ws + L.alpha), (const float*)(ws + L.dvh),
+                              (const float*)(ws + L.dgv), Bv, R, d, prescaled, d_im, st)))
+    return rc;
+  return run_grad_finalize(xt, xdt, (const float*)(ws + L.beta), (const float*)(ws + L.dth),
+                           (const float*)(ws + L.dgt), Bt, W, d, prescaled, d_s, st);
+}
+
+int dvlp_rwa_loss_fwd_bwd(const float* scores, int n_rows, int n_cols, int row_offset, int n_total, float lambda,
+                          float* loss_sum, float* d_scores, void* stream) {
+  if (!scores || !loss_sum) return DVLP_ERR_NULL_POINTER;
+  if (n_rows <= 0 || n_cols <= 0 || n_total <= 0 || row_offset < 0 || row_offset + n_rows > n_cols)
+    return DVLP_ERR_BAD_SHAPE;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_rwa_loss(scores, n_rows, n_cols, row_offset, n_total, lambda, loss_sum, d_scores, (cudaStream_t)stream);
+}
+
+int dvlp_sim_matrix_fwd(const void* a, const void* b, int N, int M, int d, float eps, int in_dtype, float* out,
+                        float* scratch, void* stream) {
+  if (!a || !b || !out || !scratch) return DVLP_ERR_NULL_POINTER;
+  if (N <= 0 || M <= 0 || d <= 0) return DVLP_ERR_BAD_SHAPE;
+  if (in_dtype != DVLP_F32 && in_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_sim_fwd(a, b, N, M, d, eps, in_dtype, out, scratch, (cudaStream_t)stream);
+}
+
+int dvlp_sim_matrix_bwd(const void* a, const void* b, int N, int M, int d, float eps, int in_dtype,
+                        const float* d_out, float* d_a, float* d_b, float* scratch, void* stream) {
+  if (!a || !b || !d_out || !scratch) return DVLP_ERR_NULL_POINTER;
+  if (N <= 0 || M <= 0 || d <= 0) return DVLP_ERR_BAD_SHAPE;
+  if (in_dtype != DVLP_F32 && in_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_sim_bwd(a, b, N, M, d, eps, in_dtype, d_out, d_a, d_b, scratch, (cudaStream_t)stream);
+}
+
+int dvlp_normsoftmax_fwd_bwd(const float* x, int N, int M, float temperature, float* loss, float* d_x,
+                             float* scratch, void* stream) {
+  if (!x || !loss || !scratch) return DVLP_ERR_NULL_POINTER;
+  if (N <= 0 || M <= 0) return DVLP_ERR_BAD_SHAPE;
+  if (!(temperature > 0.f)) return DVLP_ERR_BAD_ARG;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_normsoftmax(x, N, M, temperature, loss, d_x, scratch, (cudaStream_t)stream);
+}
+
+int dvlp_ranks_t2v(const double* sims, int Nq, int Nv, int32_t* ranks, void* stream) {
+  if (!sims || !ranks) return DVLP_ERR_NULL_POINTER;
+  if (Nq <= 0 || Nv <= 0 || Nq < Nv) return DVLP_ERR_BAD_SHAPE;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_ranks_t2v(sims, Nq, Nv, ranks, (cudaStream_t)stream);
+}
+
+int dvlp_ranks_v2t(const double* sims, int Nq, int Nv, double* ranks, void* stream) {
+  if (!sims || !ranks) return DVLP_ERR_NULL_POINTER;
+  if (Nq <= 0 || Nv <= 0 || Nq < Nv) return DVLP_ERR_BAD_SHAPE;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_ranks_v2t(sims, Nq, Nv, ranks, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// Shared device/host helpers for the demovlp_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/demovlp_b200.h"
+
+namespace dvlp {
+
+constexpr float kEps = 1e-8f;          // model/loss.py:333 l2norm eps
+constexpr float kLeaky = 0.1f;         // model/loss.py:236 LeakyReLU slope
+constexpr float kLog2e = 1.4426950408889634f;
+
+extern thread_local int g_last_cuda_error;
+void count_launch(int n = 1);
+
+#define DVLP_CUDA_OK(expr)                                   \
+  do {                                                       \
+    cudaError_t e__ = (expr);                                \
+    if (e__ != cudaSuccess) {                                \
+      dvlp::g_last_cuda_error = (int)e__;                    \
+      return DVLP_ERR_CUDA;                                  \
+    }                                                        \
+  } while (0)
+
+#define DVLP_LAUNCH_OK()                                     \
+  do {                                                       \
+    dvlp::count_launch();                                    \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) {                                \
+      dvlp::g_last_cuda_error = (int)e__;                    \
+      return DVLP_ERR_CUDA;                                  \
+    }                                                        \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeaky * x; }
+__device__ __forceinline__ float leaky_grad(float x) { return x > 0.f ? 1.f : kLeaky; }
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// Workspace layout shared by forward and backward (all offsets 256-B aligned).
+// ---------------------------------------------------------------------------
+struct Workspace {
+  // per-item prologue
+  size_t alpha, beta;        // fp32 inverse row norms 1/(|x|+eps): (Bv*R), (Bt*W)
+  size_t mterm_v, mterm_t;   // fp32 lambda*(mask - max mask) per region / word
+  size_t vh, th;             // generic: fp32 normalised rows;  tcgen05: bf16 raw rows (when input is fp32)
+  size_t gv, gt;             // Gram matrices (Bv,R,R) / (Bt,W,W): fp32 (generic) or bf16 (tcgen05)
+  // backward accumulators
+  size_t dvh, dth;           // fp32 (Bv,R,d), (Bt,W,d)
+  size_t dgv, dgt;           // fp32 (Bv,R,R), (Bt,W,W)
+  size_t scratch;            // generic kernels: per-CTA pair scratch
+  size_t total;
+  int n_cta;                 // generic kernels: persistent grid size
+  size_t scratch_per_cta;    // floats
+};
+
+Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc);
+
+// arguments of the generic pair kernels
+struct PairArgs {
+  const float *vh, *th, *gv, *gt, *mterm_v, *mterm_t;
+  int Bv, Bt, R, W, d;
+  float lambda;
+  int focal;
+  float* scores;
+  const float* d_scores;
+  float *dvh, *dth, *dgv, *dgt;
+  float* scratch;
+  size_t scratch_per_cta;
+};
+
+}  // namespace dvlp

@@ -1,0 +1,170 @@
+"""Multi-GPU (one process per GPU) version of the region-word loss.
+
+The (B x B) pair matrix is partitioned by VIDEO ROWS: rank r keeps its b = B/P videos
+and scores them against all B texts.  Text embeddings move with an all-gather, their
+gradients come back with a reduce-scatter, the row-local RWALoss partial sums meet in
+one scalar all-reduce.  Semantically this equals what the reference's
+``AllGather_multi`` pattern (trainer/trainer_dist.py:13-31) would compute if it were
+enabled in training -- every rank evaluates the loss of the CONCATENATED batch and keeps
+the gradient rows of its own shard -- without any rank ever holding the
+(B, B, R, W) tensor.
+
+torch.distributed (NCCL over NVLink on the B200 box, gloo in the CPU tests) is the
+plumbing; the arithmetic is behind the ``Backend`` hooks, which default to the CUDA
+library and are replaced by an oracle-backed stub in tests/test_dist_cpu.py.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+
+
+class CudaBackend:
+    """The shipped arithmetic: C-ABI kernels via demovlp_b200.ops."""
+
+    @staticmethod
+    def scores_fwd(im, s_all, im_m, s_m_all, lam, focal_equal, impl="auto"):
+        return ops.rw_scores_fwd_raw(ops._prep_embed(im), ops._prep_embed(s_all),
+                                     ops._prep_mask(im_m, None), ops._prep_mask(s_m_all, None),
+                                     lam, focal_equal, impl)
+
+    @staticmethod
+    def scores_bwd(state, d_scores):
+        return ops.rw_scores_bwd_raw(state, d_scores)
+
+    @staticmethod
+    def rwa_tail(scores, lam, row_offset, n_total, want_grad):
+        return ops.rwa_tail_raw(scores, lam, row_offset, n_total, want_grad)
+
+    sim_matrix = staticmethod(ops.sim_matrix)
+    norm_softmax = staticmethod(ops.norm_softmax_loss)
+
+
+_BACKEND = CudaBackend
+
+
+def set_backend(b):
+    global _BACKEND
+    _BACKEND = b
+
+
+def gather_cat(t, group=None):
+    """all_gather + cat along dim 0 in rank order (trainer_dist.py:17-22), no autograd."""
+    world = dist.get_world_size(group)
+    t = t.contiguous()
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out
+
+
+class AllGather_multi(torch.autograd.Function):
+    """Drop-in for trainer/trainer_dist.py:13-31: ``AllGather_multi.apply(tensor, n_gpu, args)``.
+
+    forward = all_gather + cat in rank order; backward = this rank's slice of the incoming
+    gradient, with no reduction (every rank is expected to have computed the same full loss).
+    ``args`` needs ``world_size`` and ``rank`` like the reference's argparse namespace.
+    """
+
+    @staticmethod
+    def forward(ctx, tensor, n_gpu, args):
+        ctx.rank = args.rank
+        ctx.batch_size = tensor.shape[0]
+        return gather_cat(tensor)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        b = ctx.batch_size
+        return grad_output[b * ctx.rank:b * (ctx.rank + 1)], None, None
+
+
+class _GatherRows(torch.autograd.Function):
+    """Same as AllGather_multi but bound to a process group instead of an args namespace."""
+
+    @staticmethod
+    def forward(ctx, tensor, group):
+        ctx.rank = dist.get_rank(group)
+        ctx.b = tensor.shape[0]
+        return gather_cat(tensor, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.b * ctx.rank:ctx.b * (ctx.rank + 1)], None
+
+
+class _ShardedRWA(torch.autograd.Function):
+    """local_loss of the concatenated batch from row shards (model/loss.py:105-116 on P ranks)."""
+
+    @staticmethod
+    def forward(ctx, im, s, im_m, s_m, lam, focal_equal, impl, group):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        b = s.shape[0]
+        if im.shape[0] != b:
+            raise RuntimeError("sharded RWALoss needs the same number of videos and texts per rank")
+        s_all = gather_cat(s.detach(), group)               # (B, W, d): the only embedding that moves
+        s_m_all = gather_cat(s_m.detach().to(torch.float32), group)
+        scores, state = _BACKEND.scores_fwd(im.detach(), s_all, im_m, s_m_all, lam, focal_equal, impl)
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        part, d_scores = _BACKEND.rwa_tail(scores, lam, rank * b, world * b, want)
+        loss = part.clone()
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)   # rows are rank-local: one scalar
+        ctx.state, ctx.d_scores, ctx.group, ctx.b = state, d_scores, group, b
+        ctx.dtypes = (im.dtype, s.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.d_scores is None:
+            raise RuntimeError("sharded RWALoss was evaluated without grad")
+        d_im, d_s_all = _BACKEND.scores_bwd(ctx.state, ctx.d_scores * g)
+        # every rank holds a partial gradient for ALL texts: sum and hand each rank its rows
+        d_s = torch.empty((ctx.b,) + tuple(d_s_all.shape[1:]), dtype=d_s_all.dtype, device=d_s_all.device)
+        dist.reduce_scatter_tensor(d_s, d_s_all.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
+        return d_im.to(ctx.dtypes[0]), d_s.to(ctx.dtypes[1]), None, None, None, None, None, None
+
+
+class ShardedGlobalLocalLoss(nn.Module):
+    """GlobalLocalLoss (model/loss.py:10-45) over the GLOBAL batch, one shard per rank.
+
+    Same constructor arguments as the reference class plus ``group``.  ``forward`` keeps the
+    six-argument signature; because the global cosine matrix needs the other ranks' CLS
+    embeddings, the first argument is the pair ``(text_cls, video_cls)`` of THIS rank's
+    (b, d) global embeddings instead of the local (b, b) ``sim_matrix`` (one-line change at
+    trainer/trainer_dist.py:160).  Returns the reference's 3-tuple; all
+    ranks return identical values.
+    """
+
+    def __init__(self, temperature=0.05, lambda_softmax=20, focal_type="prob", margin=0,
+                 max_violation=False, use_local=True, use_global=True, coef=1000., group=None, impl="auto"):
+        super().__init__()
+        self.temperature = temperature
+        self.lambda_softmax = lambda_softmax
+        self.focal_type = focal_type
+        self.use_local = use_local
+        self.use_global = use_global
+        self.cof_local = coef
+        self.group = group
+        self.impl = impl
+
+    def global_part(self, text_cls, video_cls):
+        t_all = _GatherRows.apply(text_cls, self.group)
+        v_all = _GatherRows.apply(video_cls, self.group)
+        return _BACKEND.norm_softmax(_BACKEND.sim_matrix(t_all, v_all), self.temperature)
+
+    def local_part(self, im, s, im_m, s_m):
+        return _ShardedRWA.apply(im, s, im_m, s_m, self.lambda_softmax, self.focal_type == "equal",
+                                 self.impl, self.group)
+
+    def forward(self, global_pair, local_im, local_s, local_im_m, local_s_l, local_s_m):
+        zero = torch.tensor([0.0])
+        if not self.use_local:
+            g = self.global_part(*global_pair)
+            return g, g, zero
+        if not self.use_global:
+            l = self.local_part(local_im, local_s, local_im_m, local_s_m)
+            return l, zero, l
+        g = self.global_part(*global_pair)
+        l = self.local_part(local_im, local_s, local_im_m, local_s_m)
+        return g + l, g, l

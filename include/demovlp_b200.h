@@ -1,0 +1,134 @@
+/*
+ * demovlp_b200 -- C ABI of the B200-native region-word alignment path.
+ *
+ * Drop-in boundary for the hot path of showlab/DemoVLP (reference paths are
+ * relative to the reference root).  Every entry point replaces a piece of the
+ * reference's pure-PyTorch loss/metric code; the Python host mirror in
+ * demovlp_b200/loss.py binds them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the
+ *     name ends in _host; the caller owns every buffer;
+ *   - nothing here allocates or synchronises: work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), workspace comes from the caller
+ *     (size from dvlp_rw_workspace_bytes);
+ *   - return value 0 = success, negative = DVLP_ERR_* (dvlp_error_string);
+ *   - tensors are dense row-major ("contiguous"), d is the embedding width;
+ *   - masks are the reference's ADDITIVE masks (0 = valid, -100 = padded,
+ *     trainer/trainer_dist.py:156-159), fp32;
+ *   - in_dtype: DVLP_BF16 (2-byte bfloat16) or DVLP_F32.
+ */
+#ifndef DEMOVLP_B200_H_
+#define DEMOVLP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVLP_F32 0
+#define DVLP_BF16 1
+
+#define DVLP_OK 0
+#define DVLP_ERR_BAD_SHAPE (-1)      /* non-positive or unsupported dimension            */
+#define DVLP_ERR_BAD_DTYPE (-2)      /* in_dtype is neither DVLP_F32 nor DVLP_BF16       */
+#define DVLP_ERR_NULL_POINTER (-3)   /* a required pointer is NULL                       */
+#define DVLP_ERR_MISALIGNED (-4)     /* pointer not 16-byte aligned                      */
+#define DVLP_ERR_WORKSPACE (-5)      /* workspace too small / missing                    */
+#define DVLP_ERR_CUDA (-6)           /* a CUDA call failed (see dvlp_last_cuda_error)    */
+#define DVLP_ERR_NO_DEVICE (-7)      /* no sm_100 device: there is NO CPU fallback       */
+#define DVLP_ERR_BAD_ARG (-8)        /* other invalid argument                           */
+
+/* implementation selector for the scoring kernels (debug / A-B testing) */
+#define DVLP_IMPL_AUTO 0     /* tcgen05 path when the shape qualifies, else generic    */
+#define DVLP_IMPL_GENERIC 1  /* generic-shape fp32 CUDA-core kernels                    */
+#define DVLP_IMPL_TCGEN05 2  /* tcgen05/TMEM/TMA kernels; error if shape unsupported    */
+
+int dvlp_version(void);
+const char* dvlp_error_string(int code);
+/* cudaError_t of the last failing CUDA call made by this library on this thread. */
+int dvlp_last_cuda_error(void);
+/* 1 when dvlp_rw_scores_* would take the tcgen05 path for this shape. */
+int dvlp_rw_tcgen05_supported(int R, int W, int d);
+/* process-wide default for `impl` arguments given as DVLP_IMPL_AUTO. */
+void dvlp_set_default_impl(int impl);
+/* number of kernels this library has launched so far in this process. */
+uint64_t dvlp_launch_count(void);
+
+/* Bytes of scratch dvlp_rw_scores_fwd / dvlp_rw_scores_bwd need for this shape. */
+size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl);
+
+/*
+ * Region-word pair scores, forward.
+ * Replaces RWALoss.get_sim -> xattn_score_fast -> 2 x func_attention_fast ->
+ * cosine_similarity (model/loss.py:64-71, 294-330, 209-271, 286-291).
+ *   im      (Bv, R, d)  video region embeddings        s       (Bt, W, d)  word embeddings
+ *   im_mask (Bv, R)     additive region mask           s_mask  (Bt, W)     additive word mask
+ *   lambda  = lambda_softmax (20)      focal_equal = 1 for focal_type "equal", 0 otherwise
+ *   scores  (Bv, Bt) fp32, overwritten.
+ * The workspace keeps the per-item prologue (inverse row norms, Gram matrices)
+ * that dvlp_rw_scores_bwd re-uses when called with the same workspace.
+ */
+int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, const float* s_mask,
+                       int Bv, int Bt, int R, int W, int d, float lambda, int focal_equal,
+                       int in_dtype, int impl, float* scores,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Backward of dvlp_rw_scores_fwd (what autograd does through model/loss.py:209-330):
+ * given d_scores (Bv, Bt) fp32 produces d_im (Bv, R, d) fp32 and d_s (Bt, W, d) fp32
+ * (both overwritten).  The attention tensors are recomputed, never stored.
+ * `workspace` must be the one the forward call used (same shape, inputs unchanged).
+ */
+int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, const float* s_mask,
+                       int Bv, int Bt, int R, int W, int d, float lambda, int focal_equal,
+                       int in_dtype, int impl, const float* d_scores, float* d_im, float* d_s,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * RWALoss tail (model/loss.py:108-114): KL(softmax(lambda*scores, dim=1) || eye + 1e-6).
+ * scores is the (n_rows, n_cols) block holding global rows [row_offset, row_offset+n_rows);
+ * the target 1 of local row i sits at column row_offset + i.
+ *   loss_sum  1 float, overwritten with  sum_i KL_i / n_total
+ *   d_scores  (n_rows, n_cols) or NULL:  d(loss_sum)/d(scores)
+ * Single GPU: n_rows == n_cols == n_total, row_offset 0.
+ */
+int dvlp_rwa_loss_fwd_bwd(const float* scores, int n_rows, int n_cols, int row_offset, int n_total,
+                          float lambda, float* loss_sum, float* d_scores, void* stream);
+
+/*
+ * sim_matrix (model/model.py:582-590): out[i][j] = a_i . b_j / (max(|a_i|,eps) max(|b_j|,eps)).
+ * a (N, d), b (M, d) fp32 or bf16, out (N, M) fp32.  Backward: given d_out produces d_a, d_b fp32
+ * (either may be NULL).  `scratch` holds N + M floats (inverse norms).
+ */
+int dvlp_sim_matrix_fwd(const void* a, const void* b, int N, int M, int d, float eps, int in_dtype,
+                        float* out, float* scratch, void* stream);
+int dvlp_sim_matrix_bwd(const void* a, const void* b, int N, int M, int d, float eps, int in_dtype,
+                        const float* d_out, float* d_a, float* d_b, float* scratch, void* stream);
+
+/*
+ * NormSoftmaxLoss (model/loss.py:126-138) on x (N, M) fp32:
+ *   loss = -mean diag(log_softmax(x/T, 1)) - mean diag(log_softmax(x^T/T, 1)).
+ * loss: 1 float, overwritten.  d_x (N, M) or NULL: d loss / d x.
+ * `scratch` holds N + M floats (row / column log-sum-exp).
+ */
+int dvlp_normsoftmax_fwd_bwd(const float* x, int N, int M, float temperature,
+                             float* loss, float* d_x, float* scratch, void* stream);
+
+/*
+ * Retrieval ranks (model/metric.py).  sims is the (Nq, Nv) float64 matrix the
+ * trainer builds (trainer/trainer_dist.py:369-385), rows = text queries.
+ *   t2v (metric.py:22-66):  ranks[i] = #{ j : sims[i][j] > sims[i][gt(i)] },  gt(i) = i / (Nq / Nv)
+ *   v2t (metric.py:142-189): for video v, over its captions c: #greater + (#equal-1)/2 in column v,
+ *                            minimum over c; ranks (Nv) float64.
+ * Integer / comparison work only: bit-exact with the reference.
+ */
+int dvlp_ranks_t2v(const double* sims, int Nq, int Nv, int32_t* ranks, void* stream);
+int dvlp_ranks_v2t(const double* sims, int Nq, int Nv, double* ranks, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMOVLP_B200_H_ */

@@ -1,0 +1,50 @@
+"""The kernel algebra (Gram form + hand-derived backward) against the oracle's autograd."""
+import pytest
+import torch
+
+from demovlp_b200 import synth
+from oracle import rw_oracle as O
+from tests import emul
+from tests.util import rel_err
+
+
+@pytest.mark.parametrize("focal", ["equal", "prob"])
+@pytest.mark.parametrize("shape", [(6, 80, 32, 6), (4, 30, 99, 5), (3, 17, 9, 4)])
+def test_gram_form_fp64_matches_oracle(shape, focal):
+    Bv, R, W, Bt = shape
+    b = synth.make_batch(Bv, R, W, 256, 31, 0.2, Bt=Bt)
+    im = b.im.double().requires_grad_(True); s = b.s.double().requires_grad_(True)
+    sc = O.pair_scores(im, s, b.im_mask.double(), b.s_mask.double(), focal=focal)
+    gs = torch.randn(Bv, Bt, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    (sc * gs).sum().backward()
+    sc2, d_im, d_s = emul.forward_backward(b.im.double(), b.s.double(), b.im_mask.double(),
+                                           b.s_mask.double(), gs, focal=(focal == "equal"))
+    assert (sc2 - sc.detach()).abs().max() < 1e-6      # eps placement differs at the 1e-8 level
+    assert rel_err(d_im, im.grad) < 1e-5
+    assert rel_err(d_s, s.grad) < 1e-5
+
+
+def test_bf16_rounding_budget_c1():
+    """bf16 at the tcgen05 rounding points stays inside the north-star tolerances."""
+    b = synth.make_batch(16, 80, 32, 256, 0, 0.2)
+    im = b.im.clone().requires_grad_(True); s = b.s.clone().requires_grad_(True)
+    sc = O.pair_scores(im, s, b.im_mask, b.s_mask, focal="equal")
+    loss = O.rwa_loss_from_scores(sc)
+    loss.backward()
+    sc_e = emul.forward_backward(b.im, b.s, b.im_mask, b.s_mask, bf16=True)
+    assert (sc_e - sc.detach()).abs().max() < 2e-3
+    loss_e, dsc = emul.rwa_loss_fwd_bwd(sc_e)
+    assert abs(loss_e.item() - loss.item()) < 2e-3 * max(1.0, abs(loss.item()))
+    _, d_im, d_s = emul.forward_backward(b.im, b.s, b.im_mask, b.s_mask, dsc, bf16=True)
+    assert rel_err(d_im, im.grad) < 1e-2
+    assert rel_err(d_s, s.grad) < 1e-2
+
+
+def test_rwa_tail_matches_autograd():
+    g = torch.Generator().manual_seed(0)
+    sc = (torch.randn(9, 9, generator=g, dtype=torch.float64) * 0.3).requires_grad_(True)
+    loss = O.rwa_loss_from_scores(sc)
+    loss.backward()
+    l2, d = emul.rwa_loss_fwd_bwd(sc.detach())
+    assert abs(l2.item() - loss.item()) < 1e-12
+    assert rel_err(d, sc.grad) < 1e-12
