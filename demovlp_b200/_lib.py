@@ -26,6 +26,8 @@ SYMBOLS = {
     "dvlp_rw_tcgen05_supported": (_i, [_i, _i, _i]),
     "dvlp_set_default_impl": (None, [_i]),
     "dvlp_launch_count": (C.c_uint64, []),
+    "dvlp_profile_enable": (None, [_i]),
+    "dvlp_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "dvlp_rw_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "dvlp_rw_scores_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p, _p, _sz, _p]),
     "dvlp_rw_scores_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
@@ -99,3 +101,16 @@ def dtype_code(t) -> int:
 
 def launch_count() -> int:
     return int(load().dvlp_launch_count())
+
+
+def profile_enable(on: bool):
+    load().dvlp_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{slot: (total_ms, count)} for fwd / bwd / prep / final since the last read."""
+    ms = (C.c_double * 4)()
+    cnt = (C.c_int * 4)()
+    check(load().dvlp_profile_read(ms, cnt), "profile_read")
+    names = ("fwd", "bwd", "prep", "final")
+    return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}

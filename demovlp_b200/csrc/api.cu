@@ -1,5 +1,7 @@
 // extern "C" entry points declared in include/demovlp_b200.h: validation + dispatch.
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -9,6 +11,27 @@ thread_local int g_last_cuda_error = 0;
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_default_impl{DVLP_IMPL_AUTO};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+struct ProfRec { int slot; cudaEvent_t a, b; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(int slot_, cudaStream_t st_) : slot(slot_), st(st_), rec(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  auto* r = new ProfRec{slot, nullptr, nullptr};
+  cudaEventCreate(&r->a);
+  cudaEventCreate(&r->b);
+  cudaEventRecord(r->a, st);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  auto* r = (ProfRec*)rec;
+  cudaEventRecord(r->b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(*r);
+  delete r;
+}
 
 int run_prep(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, bool, char*,
              const Workspace&, cudaStream_t);
@@ -125,6 +148,25 @@ int dvlp_rw_tcgen05_supported(int R, int W, int d) { return tc_supported(R, W, d
 void dvlp_set_default_impl(int impl) { g_default_impl.store(impl); }
 uint64_t dvlp_launch_count(void) { return g_launches.load(); }
 
+void dvlp_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+
+int dvlp_profile_read(double* ms, int* counts) {
+  if (!ms || !counts) return DVLP_ERR_NULL_POINTER;
+  for (int i = 0; i < kProfSlots; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    float e = 0.f;
+    DVLP_CUDA_OK(cudaEventSynchronize(r.b));
+    DVLP_CUDA_OK(cudaEventElapsedTime(&e, r.a, r.b));
+    ms[r.slot] += e;
+    counts[r.slot] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return DVLP_OK;
+}
+
 size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl) {
   if (Bv <= 0 || Bt <= 0 || R <= 0 || W <= 0 || d <= 0) return 0;
   bool tc = false;
@@ -146,7 +188,11 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
   if ((uintptr_t)workspace & 255) return DVLP_ERR_MISALIGNED;
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, ws, L, st))) return rc;
+  {
+    ProfScope p(kProfPrep, st);
+    if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, ws, L, st))) return rc;
+  }
+  ProfScope p(kProfFwd, st);
   if (tc) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vh);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.th);
@@ -179,6 +225,8 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   // zero the accumulators (one contiguous range: dvh .. dgt)
   DVLP_CUDA_OK(cudaMemsetAsync(ws + L.dvh, 0, L.scratch - L.dvh, st));
   int prescaled = 0;
+  {
+  ProfScope p(kProfBwd, st);
   if (tc) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vh);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.th);
@@ -196,6 +244,8 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
     a.scratch = (float*)(ws + L.scratch); a.scratch_per_cta = L.scratch_per_cta;
     if ((rc = run_pair_generic(true, a, L.n_cta, st))) return rc;
   }
+  }
+  ProfScope pf(kProfFinal, st);
   const void* xv = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.vh) : im;
   const void* xt = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.th) : s;
   int xdt = (tc && in_dtype == DVLP_F32) ? DVLP_BF16 : in_dtype;

@@ -56,6 +56,17 @@ __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162flo
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeaky * x; }
 __device__ __forceinline__ float leaky_grad(float x) { return x > 0.f ? 1.f : kLeaky; }
 
+// Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream
+// around the kernels of one slot.  Off by default; costs nothing when off.
+enum ProfSlot { kProfFwd = 0, kProfBwd = 1, kProfPrep = 2, kProfFinal = 3, kProfSlots = 4 };
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  void* rec;
+  ProfScope(int slot, cudaStream_t st);
+  ~ProfScope();
+};
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------

@@ -57,6 +57,15 @@ void dvlp_set_default_impl(int impl);
 /* number of kernels this library has launched so far in this process. */
 uint64_t dvlp_launch_count(void);
 
+/*
+ * Optional kernel timing for benchmarks: when enabled, CUDA events are recorded on the launching
+ * stream around 0 = forward pair kernel, 1 = backward pair kernel, 2 = per-item prologue,
+ * 3 = gradient finalisation.  dvlp_profile_read synchronises those events, writes the summed
+ * milliseconds and launch-group counts of the four slots (ms[4], counts[4], HOST pointers) and resets.
+ */
+void dvlp_profile_enable(int on);
+int dvlp_profile_read(double* ms_host, int* counts_host);
+
 /* Bytes of scratch dvlp_rw_scores_fwd / dvlp_rw_scores_bwd need for this shape. */
 size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl);
 

@@ -24,20 +24,28 @@ def test_gram_form_fp64_matches_oracle(shape, focal):
     assert rel_err(d_s, s.grad) < 1e-5
 
 
+TC_ROUNDING = {"gram", "q", "p", "qd"}   # where the tcgen05 path rounds to bf16 (raw operands stay exact)
+
+
 def test_bf16_rounding_budget_c1():
-    """bf16 at the tcgen05 rounding points stays inside the north-star tolerances."""
+    """bf16 at the tcgen05 rounding points stays inside the north-star tolerances.
+
+    Rounding the l2-NORMALISED operands to bf16 instead (tag "ops") was measured at 2.4e-4 on
+    scores and 1.5e-2 on gradients (lambda = 20 amplifies similarity errors) -- outside the
+    gradient budget -- which is why GEMM1 consumes the raw bf16 inputs and the inverse norms are
+    applied in fp32 afterwards."""
     b = synth.make_batch(16, 80, 32, 256, 0, 0.2)
     im = b.im.clone().requires_grad_(True); s = b.s.clone().requires_grad_(True)
     sc = O.pair_scores(im, s, b.im_mask, b.s_mask, focal="equal")
     loss = O.rwa_loss_from_scores(sc)
     loss.backward()
-    sc_e = emul.forward_backward(b.im, b.s, b.im_mask, b.s_mask, bf16=True)
-    assert (sc_e - sc.detach()).abs().max() < 2e-3
+    sc_e = emul.forward_backward(b.im, b.s, b.im_mask, b.s_mask, bf16=TC_ROUNDING)
+    assert (sc_e - sc.detach()).abs().max() < 2e-4
     loss_e, dsc = emul.rwa_loss_fwd_bwd(sc_e)
     assert abs(loss_e.item() - loss.item()) < 2e-3 * max(1.0, abs(loss.item()))
-    _, d_im, d_s = emul.forward_backward(b.im, b.s, b.im_mask, b.s_mask, dsc, bf16=True)
-    assert rel_err(d_im, im.grad) < 1e-2
-    assert rel_err(d_s, s.grad) < 1e-2
+    _, d_im, d_s = emul.forward_backward(b.im, b.s, b.im_mask, b.s_mask, dsc, bf16=TC_ROUNDING)
+    assert rel_err(d_im, im.grad) < 5e-3
+    assert rel_err(d_s, s.grad) < 5e-3
 
 
 def test_rwa_tail_matches_autograd():
