@@ -180,7 +180,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from demovlp_b200 import _lib, dist as D, loss as L, synth
+    from demovlp_b200 import _lib, dist as DD, loss as L, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,7 +206,7 @@ def run_ours(args):
     s_len = sh.s_len.to(dev)
 
     if world > 1:
-        mod = D.ShardedGlobalLocalLoss(focal_type="equal", coef=1.0).to(dev)
+        mod = DD.ShardedGlobalLocalLoss(focal_type="equal", coef=1.0).to(dev)
     else:
         mod = L.GlobalLocalLoss(focal_type="equal", coef=1.0).to(dev)
 

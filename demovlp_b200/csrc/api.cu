@@ -58,22 +58,23 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
   const size_t nv = (size_t)Bv * R, nt = (size_t)Bt * W;
+  // text-side vectors are padded to whole 128-row tiles (the tcgen05 kernel bulk-copies tiles)
+  const size_t nt_pad = (nt + 127) / 128 * 128;
   L.alpha = take(nv * 4);
-  L.beta = take(nt * 4);
+  L.beta = take(nt_pad * 4);
   L.mterm_v = take(nv * 4);
-  L.mterm_t = take(nt * 4);
-  if (tc) {
-    bool copy = in_dtype == DVLP_F32;
-    L.vh = take(copy ? nv * d * 2 : 0);
-    L.th = take(copy ? nt * d * 2 : 0);
-    L.gv = take(nv * R * 2);
-    L.gt = take(nt * W * 2);
-  } else {
-    L.vh = take(nv * d * 4);
-    L.th = take(nt * d * 4);
-    L.gv = take(nv * R * 4);
-    L.gt = take(nt * W * 4);
-  }
+  L.mterm_t = take(nt_pad * 4);
+  L.vh = take(nv * d * 4);
+  L.th = take(nt * d * 4);
+  L.gv = take(nv * R * 4);
+  L.gt = take(nt * W * 4);
+  bool copy = tc && in_dtype == DVLP_F32;
+  L.vb = take(copy ? nv * d * 2 : 0);
+  L.tb = take(copy ? nt * d * 2 : 0);
+  L.gvb = take(tc ? nv * R * 2 : 0);
+  L.gtb = take(tc ? nt_pad * W * 2 : 0);
+  L.m2v = take(tc ? nv * 4 : 0);
+  L.m2t = take(tc ? nt_pad * 4 : 0);
   L.dvh = take(nv * d * 4);
   L.dth = take(nt * d * 4);
   L.dgv = take(nv * R * 4);
@@ -194,8 +195,8 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
   }
   ProfScope p(kProfFwd, st);
   if (tc) {
-    const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vh);
-    const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.th);
+    const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
+    const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
     return run_pair_tc_fwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, st);
   }
   PairArgs a{};
@@ -227,9 +228,9 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   int prescaled = 0;
   {
   ProfScope p(kProfBwd, st);
-  if (tc) {
-    const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vh);
-    const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.th);
+  if (tc && tc_bwd_available()) {
+    const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
+    const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
     if ((rc = run_pair_tc_bwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, d_scores, ws, L, st))) return rc;
     prescaled = 1;
   } else {
@@ -246,8 +247,8 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   }
   }
   ProfScope pf(kProfFinal, st);
-  const void* xv = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.vh) : im;
-  const void* xt = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.th) : s;
+  const void* xv = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.vb) : im;
+  const void* xt = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.tb) : s;
   int xdt = (tc && in_dtype == DVLP_F32) ? DVLP_BF16 : in_dtype;
   if ((rc = run_grad_finalize(xv, xdt, (const float*)(ws + L.alpha), (const float*)(ws + L.dvh),
                               (const float*)(ws + L.dgv), Bv, R, d, prescaled, d_im, st)))

@@ -76,8 +76,12 @@ struct Workspace {
   // per-item prologue
   size_t alpha, beta;        // fp32 inverse row norms 1/(|x|+eps): (Bv*R), (Bt*W)
   size_t mterm_v, mterm_t;   // fp32 lambda*(mask - max mask) per region / word
-  size_t vh, th;             // generic: fp32 normalised rows;  tcgen05: bf16 raw rows (when input is fp32)
-  size_t gv, gt;             // Gram matrices (Bv,R,R) / (Bt,W,W): fp32 (generic) or bf16 (tcgen05)
+  size_t vh, th;             // fp32 normalised rows
+  size_t gv, gt;             // fp32 Gram matrices (Bv,R,R) / (Bt,W,W)
+  // tcgen05 extras (zero-sized otherwise)
+  size_t vb, tb;             // raw rows rounded to bf16 (only when the input is fp32)
+  size_t gvb, gtb;           // bf16 Gram matrices
+  size_t m2v, m2t;           // (mterm - lambda) * log2e
   // backward accumulators
   size_t dvh, dth;           // fp32 (Bv,R,d), (Bt,W,d)
   size_t dgv, dgt;           // fp32 (Bv,R,R), (Bt,W,W)

@@ -90,7 +90,6 @@ __device__ void dir_forward(const Dir D, const float* S, float* Q, float* Y, flo
   }
   __syncthreads();
   // (4) cos_q = num_q / sqrt(Q_q^T Y_q)
-  float csum = 0.f;
   for (int q = warp; q < D.Lq; q += nwarp) {
     float dd = 0.f;
     for (int c = lane; c < D.Lc; c += 32) {
@@ -103,10 +102,16 @@ __device__ void dir_forward(const Dir D, const float* S, float* Q, float* Y, flo
       float cs = dd > 1e-30f ? num[q] / dn : 0.f;   // cosine clamp of :291: zero context -> 0
       den[q] = dn;
       cosv[q] = cs;
-      csum += cs;
     }
   }
-  if (lane == 0) atomicAdd(red_slot, csum);
+  __syncthreads();
+  // fixed-order sum of the cosines: results do not depend on scheduling
+  if (warp == 0) {
+    float csum = 0.f;
+    for (int q = lane; q < D.Lq; q += 32) csum += cosv[q];
+    csum = warp_sum(csum);
+    if (lane == 0) *red_slot = csum;
+  }
   __syncthreads();
 }
 

@@ -250,3 +250,16 @@ def test_eval_matrix_end_to_end(impl):
     keys = [str(k) for k in e["keys"]]
     ref = dict(zip(keys, e["t2v"]))
     assert abs(got["MeanR"] - ref["MeanR"]) < 0.5
+
+
+@pytest.mark.parametrize("shape", [(16, 32, 24), (16, 48, 12), (16, 64, 8), (9, 80, 7)])
+def test_tcgen05_region_counts_and_ragged_text_tiles(shape):
+    """tcgen05 instantiations R in {32,48,64,80}; text counts that are not a multiple of the 4-text tile."""
+    Bv, R, Bt = shape
+    b = synth.make_batch(Bv, R, 32, 256, seed=17, Bt=Bt)
+    d = dev(b)
+    for focal in ("equal", "prob"):
+        want = O.pair_scores(b.im, b.s, b.im_mask, b.s_mask, focal=focal)
+        got = ops.rw_scores(d.im.to(torch.bfloat16), d.s.to(torch.bfloat16), d.im_mask, d.s_mask,
+                            focal_equal=(focal == "equal"), impl="tcgen05")
+        assert (got.cpu() - want).abs().max() < SCORE_TOL
