@@ -53,7 +53,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
 
-__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeaky * x; }
+__device__ __forceinline__ float leaky(float x) { return fmaxf(x, kLeaky * x); }
 __device__ __forceinline__ float leaky_grad(float x) { return x > 0.f ? 1.f : kLeaky; }
 
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream

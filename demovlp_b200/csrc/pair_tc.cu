@@ -223,40 +223,48 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         tmem_ld_wait();
       }
       // pass 1: S = raw * alpha_r * beta_w ; |LeakyReLU(S)|^2 over regions = this word's dir-B norm
-      float ss = 0.f;
+      // (4 independent accumulators: the chains are latency-, not throughput-bound at 2 warps/scheduler)
+      float acc4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        S[r] = S[r] * (beta_m * s_alpha[r]);
-        float l = leaky(S[r]);
-        ss = fmaf(l, l, ss);
+      for (int r = 0; r < R; r += 4) {
+        const float4 al = *reinterpret_cast<const float4*>(s_alpha + r);
+        S[r + 0] *= beta_m * al.x; S[r + 1] *= beta_m * al.y; S[r + 2] *= beta_m * al.z; S[r + 3] *= beta_m * al.w;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { float l = leaky(S[r + h]); acc4[h] = fmaf(l, l, acc4[h]); }
       }
-      s_invnB[m] = 1.f / (sqrtf(ss) + kEps);
+      s_invnB[m] = 1.f / (sqrtf((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + kEps);
       named_bar_sync(1, kGroup);             // norms exchanged between the groups
       // pass 2: A = L / n_r ; e = exp(lambda (A + mask_r) - lambda) ; focal ; numerator
-      float E = 0.f;
+      acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float av = leaky(S[r]) * s_invnA[q * R + r];
-        e[r] = ex2(fmaf(av, a.lam2, s_m2v[r]));
-        E += e[r];
+      for (int r = 0; r < R; r += 4) {
+        const float4 na = *reinterpret_cast<const float4*>(s_invnA + q * R + r);
+        const float4 mk = *reinterpret_cast<const float4*>(s_m2v + r);
+        e[r + 0] = ex2(fmaf(leaky(S[r + 0]) * na.x, a.lam2, mk.x));
+        e[r + 1] = ex2(fmaf(leaky(S[r + 1]) * na.y, a.lam2, mk.y));
+        e[r + 2] = ex2(fmaf(leaky(S[r + 2]) * na.z, a.lam2, mk.z));
+        e[r + 3] = ex2(fmaf(leaky(S[r + 3]) * na.w, a.lam2, mk.w));
+#pragma unroll
+        for (int h = 0; h < 4; ++h) acc4[h] += e[r + h];
       }
-      float num = 0.f;
+      // focal "equal": keep e_r iff e_r * R > sum_r e_r  (model/loss.py:280-282); all kept otherwise
+      const float thr = a.focal ? ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) * (1.f / R) : -1.f;
+      acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.f;
 #pragma unroll
       for (int g = 0; g < R / 8; ++g) {
         uint32_t pk[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const int r = g * 8 + h * 2;
-          float u0v = (!a.focal || e[r] * (float)R > E) ? e[r] : 0.f;
-          float u1v = (!a.focal || e[r + 1] * (float)R > E) ? e[r + 1] : 0.f;
-          pk[h] = pack_bf16(u0v, u1v);
+          pk[h] = pack_bf16(e[r] > thr ? e[r] : 0.f, e[r + 1] > thr ? e[r + 1] : 0.f);
           e[r] = bf16_lo(pk[h]);
           e[r + 1] = bf16_hi(pk[h]);
-          num = fmaf(e[r], S[r], num);
-          num = fmaf(e[r + 1], S[r + 1], num);
+          acc4[h] = fmaf(e[r], S[r], acc4[h]);
+          acc4[h] = fmaf(e[r + 1], S[r + 1], acc4[h]);
         }
         st_shared_v4(q1_row + (g >> 3) * kTileBytes + (((g & 7) ^ (m & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
       }
+      const float num = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
       fence_proxy_async();
       mbar_arrive(bar(Q1_FULL));
       // denominator: D = u^T G^V u = sum_r u_r Y1_r
@@ -270,9 +278,12 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       }
       tc_fence_before();
       mbar_arrive(bar(TM_EMPTY0 + set));      // this thread is done with TMEM set `set`
-      float Dn = 0.f;
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int r = 0; r < R; ++r) Dn = fmaf(e[r], S[r], Dn);
+      for (int r = 0; r < R; r += 4)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) d4[h] = fmaf(e[r + h], S[r + h], d4[h]);
+      const float Dn = (d4[0] + d4[1]) + (d4[2] + d4[3]);
       float cs = Dn > 1e-30f ? num * rsqrtf(Dn) : 0.f;
       cs = warp_sum(cs);                      // mean over the 32 words of text q (model/loss.py:318)
       named_bar_sync(2, kGroup);              // group B's per-text partial sums are in s_part
@@ -309,12 +320,16 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           tmem_ld16(tS2 + t * 32, reinterpret_cast<uint32_t*>(x));
           tmem_ld16(tS2 + t * 32 + 16, reinterpret_cast<uint32_t*>(x) + 16);
           tmem_ld_wait();
-          float ss = 0.f;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int w = 0; w < 32; ++w) {
-            float l = leaky(x[w] * (alpha_r * beta[t * 32 + w]));
-            ss = fmaf(l, l, ss);
+          for (int w = 0; w < 32; w += 4) {
+            const float4 be = *reinterpret_cast<const float4*>(beta + t * 32 + w);
+            float l0 = leaky(x[w] * (alpha_r * be.x)), l1 = leaky(x[w + 1] * (alpha_r * be.y));
+            float l2 = leaky(x[w + 2] * (alpha_r * be.z)), l3 = leaky(x[w + 3] * (alpha_r * be.w));
+            s4[0] = fmaf(l0, l0, s4[0]); s4[1] = fmaf(l1, l1, s4[1]);
+            s4[2] = fmaf(l2, l2, s4[2]); s4[3] = fmaf(l3, l3, s4[3]);
           }
+          const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
           if (active) s_invnA[t * R + r] = 1.f / (sqrtf(ss) + kEps);
         }
       }
@@ -326,30 +341,36 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           tmem_ld16(tS2 + t * 32, reinterpret_cast<uint32_t*>(x));
           tmem_ld16(tS2 + t * 32 + 16, reinterpret_cast<uint32_t*>(x) + 16);
           tmem_ld_wait();
-          float E = 0.f;
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int w = 0; w < 32; ++w) {
-            x[w] = x[w] * (alpha_r * beta[t * 32 + w]);
-            float av = leaky(x[w]) * s_invnB[t * 32 + w];
-            e[w] = ex2(fmaf(av, a.lam2, m2t[t * 32 + w]));
-            E += e[w];
+          for (int w = 0; w < 32; w += 4) {
+            const float4 be = *reinterpret_cast<const float4*>(beta + t * 32 + w);
+            const float4 nb = *reinterpret_cast<const float4*>(s_invnB + t * 32 + w);
+            const float4 mk = *reinterpret_cast<const float4*>(m2t + t * 32 + w);
+            x[w + 0] *= alpha_r * be.x; x[w + 1] *= alpha_r * be.y; x[w + 2] *= alpha_r * be.z; x[w + 3] *= alpha_r * be.w;
+            e[w + 0] = ex2(fmaf(leaky(x[w + 0]) * nb.x, a.lam2, mk.x));
+            e[w + 1] = ex2(fmaf(leaky(x[w + 1]) * nb.y, a.lam2, mk.y));
+            e[w + 2] = ex2(fmaf(leaky(x[w + 2]) * nb.z, a.lam2, mk.z));
+            e[w + 3] = ex2(fmaf(leaky(x[w + 3]) * nb.w, a.lam2, mk.w));
+#pragma unroll
+            for (int h = 0; h < 4; ++h) e4[h] += e[w + h];
           }
-          float nm = 0.f;
+          const float thr = a.focal ? ((e4[0] + e4[1]) + (e4[2] + e4[3])) * (1.f / kW) : -1.f;
+          float n4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t pk[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const int w = g * 8 + h * 2;
-              float u0v = (!a.focal || e[w] * (float)kW > E) ? e[w] : 0.f;
-              float u1v = (!a.focal || e[w + 1] * (float)kW > E) ? e[w + 1] : 0.f;
-              pk[h] = pack_bf16(u0v, u1v);
-              nm = fmaf(bf16_lo(pk[h]), x[w], nm);
-              nm = fmaf(bf16_hi(pk[h]), x[w + 1], nm);
+              pk[h] = pack_bf16(e[w] > thr ? e[w] : 0.f, e[w + 1] > thr ? e[w + 1] : 0.f);
+              n4[h] = fmaf(bf16_lo(pk[h]), x[w], n4[h]);
+              n4[h] = fmaf(bf16_hi(pk[h]), x[w + 1], n4[h]);
             }
             const int seg = (t & 1) * 4 + g;
             st_shared_v4(q2_row + (t >> 1) * kTileBytes + ((seg ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
+          const float nm = (n4[0] + n4[1]) + (n4[2] + n4[3]);
           num[t] = nm;
         }
       }
@@ -367,7 +388,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           tmem_ld16(tS2 + t * 32, reinterpret_cast<uint32_t*>(y));
           tmem_ld16(tS2 + t * 32 + 16, reinterpret_cast<uint32_t*>(y) + 16);
           tmem_ld_wait();
-          float Dn = 0.f;
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t pk[4];
@@ -375,10 +396,11 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             ld_shared_v4(q2_row + (t >> 1) * kTileBytes + ((seg ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              Dn = fmaf(bf16_lo(pk[h]), y[g * 8 + h * 2], Dn);
-              Dn = fmaf(bf16_hi(pk[h]), y[g * 8 + h * 2 + 1], Dn);
+              d4[h] = fmaf(bf16_lo(pk[h]), y[g * 8 + h * 2], d4[h]);
+              d4[h] = fmaf(bf16_hi(pk[h]), y[g * 8 + h * 2 + 1], d4[h]);
             }
           }
+          const float Dn = (d4[0] + d4[1]) + (d4[2] + d4[3]);
           cs[t] = (active && Dn > 1e-30f) ? num[t] * rsqrtf(Dn) : 0.f;
         }
       }
@@ -462,7 +484,6 @@ static int launch_fwd(const void* vb, const void* tb, int Bv, int Bt, float lamb
 }  // namespace tc
 
 bool tc_supported(int R, int W, int d) { return d == tc::kD && W == tc::kW && (R == 80 || R == 64 || R == 48 || R == 32); }
-bool tc_bwd_available() { return false; }
 
 int run_pair_tc_fwd(const void* vb, const void* tb, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
                     float* scores, char* ws, const Workspace& L, cudaStream_t st) {
@@ -475,7 +496,4 @@ int run_pair_tc_fwd(const void* vb, const void* tb, int Bv, int Bt, int R, int W
   }
   return DVLP_ERR_BAD_SHAPE;
 }
-int run_pair_tc_bwd(const void*, const void*, int, int, int, int, int, float, int, const float*, char*,
-                    const Workspace&, cudaStream_t) { return DVLP_ERR_BAD_SHAPE; }
-
 }  // namespace dvlp

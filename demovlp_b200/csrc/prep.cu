@@ -123,6 +123,12 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
   }
   const __nv_bfloat16* vb = (const __nv_bfloat16*)im;
   const __nv_bfloat16* tb = (const __nv_bfloat16*)s;
+  {
+    // text-side vectors are read in whole 128-row tiles: keep the padded tail finite
+    const size_t nt_pad = ((size_t)Bt * W + 127) / 128 * 128;
+    DVLP_CUDA_OK(cudaMemsetAsync(ws + L.beta, 0, nt_pad * 4, st));
+    DVLP_CUDA_OK(cudaMemsetAsync(ws + L.m2t, 0, nt_pad * 4, st));
+  }
   if (in_dtype == DVLP_F32) {
     size_t nv = (size_t)Bv * R * d, nt = (size_t)Bt * W * d;
     k_to_bf16<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>((const float*)im, nv, (__nv_bfloat16*)(ws + L.vb));

@@ -1,0 +1,23 @@
+"""Runs the fused forward (and optionally backward) at the config-2 shape a few times: a short target for ncu."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from demovlp_b200 import ops, synth, _lib
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+bwd = len(sys.argv) > 2 and sys.argv[2] == "bwd"
+b = synth.make_batch(B, 80, 32, 256, seed=1).to("cuda")
+im, s = b.im.to(torch.bfloat16), b.s.to(torch.bfloat16)
+g = torch.randn(B, B, device="cuda")
+for it in range(3):
+    sc, st = ops.rw_scores_fwd_raw(im, s, b.im_mask, b.s_mask, 20.0, 1, "auto")
+    if bwd:
+        ops.rw_scores_bwd_raw(st, g)
+torch.cuda.synchronize()
+_lib.profile_enable(True)
+for it in range(10):
+    sc, st = ops.rw_scores_fwd_raw(im, s, b.im_mask, b.s_mask, 20.0, 1, "auto")
+    if bwd:
+        ops.rw_scores_bwd_raw(st, g)
+torch.cuda.synchronize()
+print({k: (round(v[0] / max(v[1], 1) * 1e3, 1), v[1]) for k, v in _lib.profile_read().items()}, "us per launch")
