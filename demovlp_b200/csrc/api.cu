@@ -33,7 +33,7 @@ ProfScope::~ProfScope() {
   delete r;
 }
 
-int run_prep(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, bool, char*,
+int run_prep(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, bool, bool, char*,
              const Workspace&, cudaStream_t);
 int run_pair_generic(bool backward, const PairArgs& a, int n_cta, cudaStream_t st);
 int run_grad_finalize(const void*, int, const float*, const float*, const float*, int, int, int, int, float*,
@@ -191,7 +191,7 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope p(kProfPrep, st);
-    if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, ws, L, st))) return rc;
+    if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, tc && !tc_bwd_available(), ws, L, st))) return rc;
   }
   ProfScope p(kProfFwd, st);
   if (tc) {

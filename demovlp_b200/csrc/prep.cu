@@ -77,6 +77,56 @@ __global__ void k_gram(const Tin* __restrict__ x, const float* __restrict__ inv,
   }
 }
 
+// Fast Gram for the tcgen05 path (bf16 rows, d == 256, L <= 128): the item's rows are staged once in
+// shared memory as fp32 (row stride d+1 words: conflict-free) and each thread owns 4x4 blocks of G.
+__global__ void __launch_bounds__(256) k_gram_tile(const __nv_bfloat16* __restrict__ x, const float* __restrict__ inv,
+                                                   int L, int d, float* __restrict__ G, __nv_bfloat16* __restrict__ Gb) {
+  extern __shared__ float xs[];                 // [L][d + 1], rows pre-scaled by inv
+  const int item = blockIdx.x;
+  const __nv_bfloat16* X = x + (size_t)item * L * d;
+  const float* iv = inv + (size_t)item * L;
+  const int ld = d + 1;
+  for (int e = threadIdx.x; e < L * d / 2; e += blockDim.x) {
+    const int row = (2 * e) / d, col = (2 * e) - row * d;
+    const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(X)[e];
+    const float a = iv[row];
+    xs[row * ld + col] = __bfloat162float(v.x) * a;
+    xs[row * ld + col + 1] = __bfloat162float(v.y) * a;
+  }
+  __syncthreads();
+  const int nb = (L + 3) / 4;
+  for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
+    // block (ab, bb) owns rows {ab + h*nb} x columns {bb + h*nb}: consecutive threads read consecutive
+    // shared-memory rows (row stride d+1 words), i.e. distinct banks
+    const int ab = blk / nb, bb = blk % nb;
+    if (bb < ab) continue;                      // symmetric: compute the upper blocks, mirror on store
+    float acc[4][4] = {};
+    int ra[4], rb[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) { ra[h] = min(ab + h * nb, L - 1) * ld; rb[h] = min(bb + h * nb, L - 1) * ld; }
+    for (int k = 0; k < d; ++k) {
+      float va[4], vb[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) { va[h] = xs[ra[h] + k]; vb[h] = xs[rb[h] + k]; }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(va[p], vb[q], acc[p][q]);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int aa = ab + p * nb, bq = bb + q * nb;
+        if (aa < L && bq < L) {
+          const size_t i1 = (size_t)item * L * L + (size_t)aa * L + bq, i2 = (size_t)item * L * L + (size_t)bq * L + aa;
+          if (G) { G[i1] = acc[p][q]; G[i2] = acc[p][q]; }
+          if (Gb) { Gb[i1] = __float2bfloat16(acc[p][q]); Gb[i2] = __float2bfloat16(acc[p][q]); }
+        }
+      }
+  }
+}
+
 template <typename Tin>
 static int prep_side(const Tin* x, const float* mask, int items, int L, int d, float lambda, float* inv,
                      float* mterm, float* mterm2, float* xh, float* G, __nv_bfloat16* Gb, cudaStream_t st) {
@@ -100,7 +150,7 @@ __global__ void k_to_bf16(const float* __restrict__ x, size_t n, __nv_bfloat16* 
 // tcgen05 kernels read are produced as well, and fp32 inputs are first rounded to bf16 ("bf16 in")
 // so that every later stage sees exactly the operands the tensor cores see.
 int run_prep(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
-             int R, int W, int d, float lambda, int in_dtype, bool tc, char* ws, const Workspace& L,
+             int R, int W, int d, float lambda, int in_dtype, bool tc, bool full, char* ws, const Workspace& L,
              cudaStream_t st) {
   float* alpha = (float*)(ws + L.alpha);
   float* beta = (float*)(ws + L.beta);
@@ -138,11 +188,32 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
     vb = (const __nv_bfloat16*)(ws + L.vb);
     tb = (const __nv_bfloat16*)(ws + L.tb);
   }
-  int rc = prep_side(vb, im_mask, Bv, R, d, lambda, alpha, mv, (float*)(ws + L.m2v), vh, gv,
-                     (__nv_bfloat16*)(ws + L.gvb), st);
-  if (rc) return rc;
-  return prep_side(tb, s_mask, Bt, W, d, lambda, beta, mt, (float*)(ws + L.m2t), th, gt,
-                   (__nv_bfloat16*)(ws + L.gtb), st);
+  // lean tcgen05 prologue: inverse norms, mask terms (natural + log2 domain), bf16 Gram.  The fp32
+  // normalised rows / fp32 Gram of the generic kernels are produced only when `full` is set
+  // (generic backward requested for a tcgen05 forward: DVLP_TC_BWD=0).
+  struct Side { const __nv_bfloat16* x; const float* mask; int items, Lc; float *inv, *mt, *m2, *xh, *G; __nv_bfloat16* Gb; };
+  Side sides[2] = {{vb, im_mask, Bv, R, alpha, mv, (float*)(ws + L.m2v), vh, gv, (__nv_bfloat16*)(ws + L.gvb)},
+                   {tb, s_mask, Bt, W, beta, mt, (float*)(ws + L.m2t), th, gt, (__nv_bfloat16*)(ws + L.gtb)}};
+  for (const Side& sd : sides) {
+    const int rows = sd.items * sd.Lc;
+    k_prep_rows<__nv_bfloat16><<<(rows + 7) / 8, 256, 0, st>>>(sd.x, rows, d, sd.inv, full ? sd.xh : nullptr, nullptr);
+    DVLP_LAUNCH_OK();
+    k_mask_terms<<<(sd.items + 7) / 8, 256, 0, st>>>(sd.mask, sd.items, sd.Lc, lambda, sd.mt, sd.m2);
+    DVLP_LAUNCH_OK();
+    const size_t smem = (size_t)sd.Lc * (d + 1) * 4;
+    if (smem <= 200 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        DVLP_CUDA_OK(cudaFuncSetAttribute(k_gram_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+      }
+      k_gram_tile<<<sd.items, 256, smem, st>>>(sd.x, sd.inv, sd.Lc, d, full ? sd.G : nullptr, sd.Gb);
+    } else {
+      k_gram<__nv_bfloat16><<<sd.items, 256, 0, st>>>(sd.x, sd.inv, sd.Lc, d, sd.G, sd.Gb);
+    }
+    DVLP_LAUNCH_OK();
+  }
+  return DVLP_OK;
 }
 
 }  // namespace dvlp

@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(1024) k_sim_fwd(const T* __restrict__ a, const
   if (i < N && j < M) out[(size_t)i * M + j] = acc * ia[i] * ib[j];
 }
 
+constexpr int kSimRB = 2;   // rows of `a` per CTA (small: the matrices are small, parallelism matters)
+
 // d_a[i] = inv_i ( g_i - an_i (an_i . g_i) ),  g_i = sum_j w[i][j] bn_j,  w = d_out (TRANS: d_out^T)
 // valid for |a_i| >= eps; a row shorter than eps is scaled by the constant 1/eps instead.
 template <typename T, bool TRANS>
@@ -151,8 +153,8 @@ __global__ void __launch_bounds__(256) k_sim_bwd_side(const T* __restrict__ a, c
                                                       int d, float eps, const float* __restrict__ ia,
                                                       const float* __restrict__ ib, const float* __restrict__ d_out,
                                                       float* __restrict__ d_a) {
-  // this CTA: 8 rows of `a`, all d columns (thread k strides d)
-  constexpr int RB = 8;
+  // this CTA: RB rows of `a`, all d columns (thread k strides d)
+  constexpr int RB = kSimRB;
   __shared__ float red[RB][8];
   const int i0 = blockIdx.x * RB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -304,11 +306,11 @@ static int sim_bwd_t(const T* a, const T* b, int N, int M, int d, float eps, con
   k_inv_norm_max<T><<<(M + 7) / 8, 256, 0, st>>>(b, M, d, eps, ib);
   DVLP_LAUNCH_OK();
   if (d_a) {
-    k_sim_bwd_side<T, false><<<(N + 7) / 8, 256, 0, st>>>(a, b, N, M, d, eps, ia, ib, d_out, d_a);
+    k_sim_bwd_side<T, false><<<(N + kSimRB - 1) / kSimRB, 256, 0, st>>>(a, b, N, M, d, eps, ia, ib, d_out, d_a);
     DVLP_LAUNCH_OK();
   }
   if (d_b) {
-    k_sim_bwd_side<T, true><<<(M + 7) / 8, 256, 0, st>>>(b, a, M, N, d, eps, ib, ia, d_out, d_b);
+    k_sim_bwd_side<T, true><<<(M + kSimRB - 1) / kSimRB, 256, 0, st>>>(b, a, M, N, d, eps, ib, ia, d_out, d_b);
     DVLP_LAUNCH_OK();
   }
   return DVLP_OK;

@@ -1,0 +1,69 @@
+"""Multi-GPU (NCCL) check of the sharded loss on the real kernels: 2 ranks, global batch 2*b, against
+the single-GPU loss of the concatenated batch (the semantics of trainer/trainer_dist.py:13-31)."""
+import os
+import socket
+import sys
+import tempfile
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir, b):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from demovlp_b200 import dist as D, synth
+    full = synth.make_batch(world * b, 80, 32, 256, seed=2)
+    sh = full.rows(rank * b, (rank + 1) * b).to(f"cuda:{rank}")
+    im = sh.im.to(torch.bfloat16).requires_grad_(True)
+    s = sh.s.to(torch.bfloat16).requires_grad_(True)
+    gt = sh.g_text.clone().requires_grad_(True)
+    gv = sh.g_vid.clone().requires_grad_(True)
+    mod = D.ShardedGlobalLocalLoss(focal_type="equal", coef=1.0)
+    loss, g, l = mod((gt, gv), im, s, sh.im_mask, sh.s_len, sh.s_mask)
+    loss.backward()
+    torch.cuda.synchronize()
+    torch.save(dict(loss=loss.detach().cpu(), g=g.detach().cpu(), l=l.detach().cpu(), d_im=im.grad.float().cpu(),
+                    d_s=s.grad.float().cpu(), d_gt=gt.grad.cpu(), d_gv=gv.grad.cpu()),
+               os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_loss_two_gpus_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from demovlp_b200 import loss as L, synth
+    from tests.util import rel_err
+    world, b = 2, 16
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker, args=(world, port, td, b), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(td, f"rank{r}.pt")) for r in range(world)]
+    full = synth.make_batch(world * b, 80, 32, 256, seed=2).to("cuda:0")
+    im = full.im.to(torch.bfloat16).requires_grad_(True)
+    s = full.s.to(torch.bfloat16).requires_grad_(True)
+    gt = full.g_text.clone().requires_grad_(True)
+    gv = full.g_vid.clone().requires_grad_(True)
+    mod = L.GlobalLocalLoss(focal_type="equal", coef=1.0)
+    loss, g, l = mod(L.sim_matrix(gt, gv), im, s, full.im_mask, full.s_len, full.s_mask)
+    loss.backward()
+    for r, o in enumerate(outs):
+        sl = slice(r * b, (r + 1) * b)
+        assert abs(o["loss"].item() - loss.item()) < 1e-4 * max(1, abs(loss.item()))
+        assert abs(o["l"].item() - l.item()) < 1e-4 * max(1, abs(l.item()))
+        assert rel_err(o["d_im"], im.grad.float().cpu()[sl]) < 1e-2
+        assert rel_err(o["d_s"], s.grad.float().cpu()[sl]) < 1e-2
+        assert rel_err(o["d_gt"], gt.grad.cpu()[sl]) < 1e-4
+        assert rel_err(o["d_gv"], gv.grad.cpu()[sl]) < 1e-4

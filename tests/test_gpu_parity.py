@@ -136,8 +136,9 @@ def test_size_independent_properties_full_size(impl):
         a1, b1 = ops.rw_scores_bwd_raw(st, g1)
         a2, b2 = ops.rw_scores_bwd_raw(st, g2)
         a3, b3 = ops.rw_scores_bwd_raw(st, g1 + 2 * g2)
-        assert rel_err(a3, a1 + 2 * a2) < 2e-3
-        assert rel_err(b3, b1 + 2 * b2) < 2e-3
+        # (the tcgen05 path rounds the dS operand of the gradient GEMMs to bf16: linear to ~2^-9)
+        assert rel_err(a3, a1 + 2 * a2) < 6e-3
+        assert rel_err(b3, b1 + 2 * b2) < 6e-3
 
 
 def test_mask_dtype_and_missing_cap_mask():
