@@ -27,9 +27,9 @@ namespace dvlp {
 using namespace ptx;
 
 namespace tc {
-constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128, kThreads = 320;
+constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128, kThreads = 512;
 constexpr int kTileBytes = 16384;   // 128 rows x 128 B: one K-chunk (64 bf16) of a 128-row operand tile
-constexpr int kGroup = 256;         // threads of group A + group B (named barriers)
+constexpr int kGroup = 384;         // threads of group A + both halves of group B (named barriers)
 
 template <int R>
 struct Lay {
@@ -95,8 +95,9 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     prefetch_tmap(&mapV); prefetch_tmap(&mapT); prefetch_tmap(&mapGV); prefetch_tmap(&mapGT);
     for (int i = 0; i < kNumBars; ++i) {
       uint32_t cnt = 1;
-      if (i == Q1_FULL || i == Q2_FULL) cnt = 128;
-      if (i == TM_EMPTY0 || i == TM_EMPTY1) cnt = 256;
+      if (i == Q1_FULL) cnt = 128;
+      if (i == Q2_FULL) cnt = 256;
+      if (i == TM_EMPTY0 || i == TM_EMPTY1) cnt = 384;
       mbar_init(bar(i), cnt);
     }
     fence_mbar_init();
@@ -114,7 +115,9 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
   auto tile_of = [&](int k) { return (int)((u0 + k) % a.tiles_per_video); };
   auto is_switch = [&](int k) { return k == 0 || video_of(k) != video_of(k - 1); };
 
-  if (warp == 0) {
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       for (int k = 0; k < n_tiles; ++k) {
@@ -150,18 +153,18 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       tc_fence_after();
       if (lane == 0) {
         const uint32_t dS1 = tmem + set * 256, dS2 = tmem + set * 256 + 128;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            mma_bf16(dS1, smem_desc_sw128(sbase + L::T + c * kTileBytes + s * 32, 1024),
-                     smem_desc_sw128(sbase + L::V + c * L::kVChunk + s * 32, 1024), idS1, (c | s) != 0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            mma_bf16(dS2, smem_desc_sw128(sbase + L::V + c * L::kVChunk + s * 32, 1024),
-                     smem_desc_sw128(sbase + L::T + c * kTileBytes + s * 32, 1024), idS2, (c | s) != 0);
+#pragma unroll 1
+        for (int ks = 0; ks < 16; ++ks) {
+          const uint32_t c = ks >> 2, sub = (ks & 3) * 32;
+          mma_bf16(dS1, smem_desc_sw128(sbase + L::T + c * kTileBytes + sub, 1024),
+                   smem_desc_sw128(sbase + L::V + c * L::kVChunk + sub, 1024), idS1, ks != 0);
+        }
+#pragma unroll 1
+        for (int ks = 0; ks < 16; ++ks) {
+          const uint32_t c = ks >> 2, sub = (ks & 3) * 32;
+          mma_bf16(dS2, smem_desc_sw128(sbase + L::V + c * L::kVChunk + sub, 1024),
+                   smem_desc_sw128(sbase + L::T + c * kTileBytes + sub, 1024), idS2, ks != 0);
+        }
         tc_commit(bar(S_FULL0 + set));
         tc_commit(bar(T_EMPTY));
       }
@@ -177,7 +180,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       mbar_wait(bar(Q1_FULL), k & 1);
       tc_fence_after();
       if (lane == 0) {
-#pragma unroll
+#pragma unroll 1
         for (int s = 0; s < R / 16; ++s)
           mma_bf16(tmem + set * 256, smem_desc_sw128(sbase + L::Q1 + (s / 4) * kTileBytes + (s % 4) * 32, 1024),
                    smem_desc_sw128(sbase + L::GV + (s / 4) * L::kVChunk + (s % 4) * 32, 1024), idS1, s != 0);
@@ -189,9 +192,9 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       mbar_wait(bar(GT_FULL0 + set), (k >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < kTPT; ++t)
-#pragma unroll
+#pragma unroll 1
           for (int s = 0; s < 2; ++s)
             mma_bf16(tmem + set * 256 + 128 + t * 32,
                      smem_desc_sw128(sbase + L::Q2 + (t / 2) * kTileBytes + (t % 2) * 64 + s * 32, 1024),
@@ -201,8 +204,10 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       __syncwarp();
       if (more && !ahead) issue_S(k + 1);
     }
-  } else if (warp < 6) {
+   }
+  } else if (warp < 8) {
     // ================== group A: i2t direction, thread = word row ==================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int q = warp & 3;                 // TMEM lane quadrant of this warp == text slot of the tile
     const int m = q * 32 + lane;            // word row of the tile
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -294,6 +299,9 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     }
   } else {
     // ================= group B: t2i direction, thread = region row =================
+    // two halves (warps 8-11: texts 0,1 of the tile; warps 12-15: texts 2,3) double the resident warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    const int t_lo = (warp >= 12) ? 2 : 0;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const bool warp_active = q * 32 < R;      // warps whose 32 rows are all padding only keep the protocol going
@@ -311,11 +319,12 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       const float* beta = s_beta + set * 128;
       const float* m2t = s_m2t + set * 128;
       const uint32_t tS2 = tmem + set * 256 + 128 + lane_off;
-      float num[kTPT];
+      float num[2];
       if (warp_active) {
         // pass 1: per text, |LeakyReLU(S)|^2 over its 32 words = this region's dir-A norm
 #pragma unroll
-        for (int t = 0; t < kTPT; ++t) {
+        for (int tt = 0; tt < 2; ++tt) {
+          const int t = t_lo + tt;
           float x[32];
           tmem_ld16(tS2 + t * 32, reinterpret_cast<uint32_t*>(x));
           tmem_ld16(tS2 + t * 32 + 16, reinterpret_cast<uint32_t*>(x) + 16);
@@ -336,7 +345,8 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       named_bar_sync(1, kGroup);
       if (warp_active) {
 #pragma unroll
-        for (int t = 0; t < kTPT; ++t) {
+        for (int tt = 0; tt < 2; ++tt) {
+          const int t = t_lo + tt;
           float x[32], e[32];
           tmem_ld16(tS2 + t * 32, reinterpret_cast<uint32_t*>(x));
           tmem_ld16(tS2 + t * 32 + 16, reinterpret_cast<uint32_t*>(x) + 16);
@@ -371,19 +381,18 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             st_shared_v4(q2_row + (t >> 1) * kTileBytes + ((seg ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
           const float nm = (n4[0] + n4[1]) + (n4[2] + n4[3]);
-          num[t] = nm;
+          num[tt] = nm;
         }
       }
       fence_proxy_async();
       mbar_arrive(bar(Q2_FULL));
       mbar_wait(bar(Y2_FULL0 + set), (k >> 1) & 1);
       tc_fence_after();
-      float cs[kTPT];
-#pragma unroll
-      for (int t = 0; t < kTPT; ++t) cs[t] = 0.f;
+      float cs[2] = {0.f, 0.f};
       if (warp_active) {
 #pragma unroll
-        for (int t = 0; t < kTPT; ++t) {
+        for (int tt = 0; tt < 2; ++tt) {
+          const int t = t_lo + tt;
           float y[32];
           tmem_ld16(tS2 + t * 32, reinterpret_cast<uint32_t*>(y));
           tmem_ld16(tS2 + t * 32 + 16, reinterpret_cast<uint32_t*>(y) + 16);
@@ -401,15 +410,15 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             }
           }
           const float Dn = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-          cs[t] = (active && Dn > 1e-30f) ? num[t] * rsqrtf(Dn) : 0.f;
+          cs[tt] = (active && Dn > 1e-30f) ? num[tt] * rsqrtf(Dn) : 0.f;
         }
       }
       tc_fence_before();
       mbar_arrive(bar(TM_EMPTY0 + set));
 #pragma unroll
-      for (int t = 0; t < kTPT; ++t) {
-        float v = warp_sum(cs[t]);
-        if (lane == 0) s_part[q * 4 + t] = v;
+      for (int tt = 0; tt < 2; ++tt) {
+        float v = warp_sum(cs[tt]);
+        if (lane == 0) s_part[q * 4 + t_lo + tt] = v;
       }
       named_bar_sync(2, kGroup);
     }

@@ -17,8 +17,8 @@
 // orientation) are done with warp-shuffle transpose-reductions.
 // Gradient tiles are flushed from TMEM with vector red.global adds (accumulators live in L2).
 //
-// Warp roles (384 threads, 3 warpgroups, registers re-split with setmaxnreg):
-//   WG0: warp 0 TMA producer, warp 1 MMA issuer;  WG1: group A;  WG2: group B.
+// Warp roles (512 threads, 4 warpgroups, registers re-split with setmaxnreg):
+//   WG0: warp 0 TMA producer, warp 1 MMA issuer;  WG1: group A;  WG2 / WG3: group B for texts 0,1 / 2,3 of the tile.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -28,9 +28,9 @@ namespace dvlp {
 using namespace ptx;
 
 namespace tcb {
-constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128, kThreads = 384;
+constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128, kThreads = 512;
 constexpr int kTileBytes = 16384;
-constexpr int kGroup = 256;
+constexpr int kGroup = 384;
 
 template <int R>
 struct Lay {
@@ -51,11 +51,11 @@ struct Lay {
   static constexpr int INVNA = M2T + 512;           // [4][R]
   static constexpr int INVNB = INVNA + 4 * R * 4;   // [128]
   static constexpr int TA = INVNB + 512;            // [4][R]   sum_w A dA per (text, region)
-  static constexpr int TBP = TA + 4 * R * 4;        // [2][4][32] per-warp partials of sum_r A dA
-  static constexpr int BARS = TBP + 1024;
+  static constexpr int TBP = TA + 4 * R * 4;        // [4 texts][4 warps][32] per-warp partials of sum_r A dA
+  static constexpr int BARS = TBP + 2048;
   static constexpr int TMEMPTR = BARS + 16 * 8;
   static constexpr int kBytes = TMEMPTR + 16;
-  static constexpr int kAlloc = kBytes + 1024;
+  static constexpr int kAlloc = kBytes;             // dynamic shared memory starts 1024-B aligned (checked at run time)
   static_assert(kAlloc <= 232448, "shared memory budget");
 };
 
@@ -119,9 +119,10 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
               const __grid_constant__ CUtensorMap mapGV, const __grid_constant__ CUtensorMap mapGT, Args a) {
   using L = Lay<R>;
   static_assert(R % 16 == 0 && R >= 16 && R <= 128, "R must be a multiple of 16 in [16,128]");
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (sbase & 1023u) __trap();          // the 128-byte-swizzle tiles need a 1024-byte aligned base
+  uint8_t* sgen = smem_raw;
   float* s_alpha = (float*)(sgen + L::ALPHA);
   float* s_m2v = (float*)(sgen + L::M2V);
   float* s_beta = (float*)(sgen + L::BETA);
@@ -142,7 +143,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     prefetch_tmap(&mapV); prefetch_tmap(&mapT); prefetch_tmap(&mapGV); prefetch_tmap(&mapGT);
     for (int i = 0; i < kNumBars; ++i) {
       uint32_t cnt = 1;
-      if (i == U_READY || i == UD_READY || i == P_READY || i == SCRATCH_FREE) cnt = 256;
+      if (i == U_READY || i == UD_READY || i == P_READY || i == SCRATCH_FREE) cnt = 384;
       mbar_init(bar(i), cnt);
     }
     fence_mbar_init();
@@ -277,7 +278,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     }
   } else if (warp < 8) {
     // ================== group A: i2t direction, thread = word row ==================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -460,7 +461,9 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     }
   } else {
     // ================= group B: t2i direction, thread = region row =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    // two halves (warps 8-11: texts 0,1; warps 12-15: texts 2,3): twice the resident warps, half the chain
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    const int hb = (warp >= 12) ? 1 : 0, t_lo = hb * 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const bool warp_active = q * 32 < R;
@@ -480,10 +483,11 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       mbar_wait(bar(S_DONE), ph);
       tc_fence_after();
       const float alpha_r = active ? s_alpha[r] : 0.f;
-      float num[kTPT], c1v[kTPT], kapv[kTPT];
+      float num[2], c1v[2], kapv[2];
       if (warp_active) {
 #pragma unroll
-        for (int t = 0; t < kTPT; ++t) {
+        for (int tt = 0; tt < 2; ++tt) {
+          const int t = t_lo + tt;
           float x[32];
           tmem_ld16(tmem + cS2 + lane_off + t * 32, reinterpret_cast<uint32_t*>(x));
           tmem_ld16(tmem + cS2 + lane_off + t * 32 + 16, reinterpret_cast<uint32_t*>(x) + 16);
@@ -503,7 +507,8 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       named_bar_sync(1, kGroup);
       if (warp_active) {
 #pragma unroll
-        for (int t = 0; t < kTPT; ++t) {
+        for (int tt = 0; tt < 2; ++tt) {
+          const int t = t_lo + tt;
           float x[32], e[32];
           tmem_ld16(tmem + cS2 + lane_off + t * 32, reinterpret_cast<uint32_t*>(x));
           tmem_ld16(tmem + cS2 + lane_off + t * 32 + 16, reinterpret_cast<uint32_t*>(x) + 16);
@@ -536,7 +541,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             }
             if (active) st_shared_v4(seg_addr(sbase + L::B1, t, g4), pk[0], pk[1], pk[2], pk[3]);
           }
-          num[t] = (n4[0] + n4[1]) + (n4[2] + n4[3]);
+          num[tt] = (n4[0] + n4[1]) + (n4[2] + n4[3]);
         }
       }
       fence_proxy_async();
@@ -546,7 +551,8 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       tc_fence_after();
       if (warp_active) {
 #pragma unroll
-        for (int t = 0; t < kTPT; ++t) {
+        for (int tt = 0; tt < 2; ++tt) {
+          const int t = t_lo + tt;
           const int j = jt * kTPT + t;
           const float g = j < a.Bt ? a.d_scores[(size_t)i * a.Bt + j] : 0.f;
           float y[32];
@@ -567,10 +573,10 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           const float Dn = (d4[0] + d4[1]) + (d4[2] + d4[3]);
           const bool ok = active && Dn > 1e-30f;
           const float rden = ok ? rsqrtf(Dn) : 0.f;
-          const float cosv = num[t] * rden;
+          const float cosv = num[tt] * rden;
           const float gam = g * (1.f / R);
-          c1v[t] = ok ? gam * rden : 0.f;
-          kapv[t] = ok ? cosv * rden : 0.f;
+          c1v[tt] = ok ? gam * rden : 0.f;
+          kapv[tt] = ok ? cosv * rden : 0.f;
           const float dD = ok ? -0.5f * gam * cosv * rden * rden : 0.f;
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
@@ -586,12 +592,11 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       mbar_arrive(bar(UD_READY));
       // ---- loop B: per text, dA, the cross-region sum t_w = sum_r A dA, dS, P2
 #pragma unroll 1
-      for (int t = 0; t < kTPT; ++t) {
+      for (int tt = 0; tt < 2; ++tt) {
+        const int t = t_lo + tt;
         float x[32], dA[32];
         uint32_t pk[16];
-        float c1 = 0.f, kap = 0.f;
-#pragma unroll
-        for (int tt = 0; tt < kTPT; ++tt) { if (tt == t) { c1 = c1v[tt]; kap = kapv[tt]; } }
+        const float c1 = tt ? c1v[1] : c1v[0], kap = tt ? kapv[1] : kapv[0];
         if (warp_active) {
           float y[32];
           tmem_ld16(tmem + cS2 + lane_off + t * 32, reinterpret_cast<uint32_t*>(x));
@@ -612,14 +617,14 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             v[w] = active ? leaky(x[w]) * s_invnB[t * 32 + w] * dA[w] : 0.f;
           }
           const float part = lanes_to_columns32(v, lane);
-          s_tBp[((t & 1) * 4 + q) * 32 + lane] = part;
+          s_tBp[(t * 4 + q) * 32 + lane] = part;
         } else {
-          s_tBp[((t & 1) * 4 + q) * 32 + lane] = 0.f;
+          s_tBp[(t * 4 + q) * 32 + lane] = 0.f;
         }
-        named_bar_sync(3, 128);
-        if (t == 0) mbar_wait(bar(DG_DONE), ph);       // U2 / UD2 consumed: B1 may take P2
+        named_bar_sync(3 + hb, 128);                   // the four region-quadrant warps of this half
+        if (tt == 0) mbar_wait(bar(DG_DONE), ph);      // U2 / UD2 consumed: B1 may take P2
         if (warp_active) {
-          const float* tb = s_tBp + (t & 1) * 128;
+          const float* tb = s_tBp + t * 128;
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
             uint32_t o[4];
@@ -647,7 +652,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       if (warp_active) {
         float* dst = a.dgv + ((size_t)i * R + r) * R;
 #pragma unroll 1
-        for (int c = 0; c < R; c += 16) {
+        for (int c = hb * 16; c < R; c += 32) {         // the two halves take alternate 16-column chunks
           float v[16];
           tmem_ld16(tmem + cS1 + lane_off + c, reinterpret_cast<uint32_t*>(v));
           tmem_ld_wait();
@@ -666,7 +671,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       if (warp_active) {
         float* dst = a.dvh + ((size_t)i * R + r) * kD;
 #pragma unroll 1
-        for (int c = 0; c < kD; c += 32) {
+        for (int c = hb * 32; c < kD; c += 64) {        // the two halves take alternate 32-column chunks
           float v[32];
           tmem_ld16(tmem + cDV + lane_off + c, reinterpret_cast<uint32_t*>(v));
           tmem_ld16(tmem + cDV + lane_off + c + 16, reinterpret_cast<uint32_t*>(v) + 16);

@@ -37,16 +37,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
-  printf("demovlp_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
-         parity);
-  __trap();
-}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  (No function call
+// here: an ABI call inside a setmaxnreg kernel caps every role at the smallest register budget.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) mbar_timeout(bar, parity);
+    if (++spins > (1u << 24)) __trap();
   }
 }
 
