@@ -52,6 +52,9 @@ int run_pair_tc_fwd(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int
 int run_pair_tc_bwd(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
                     int focal, const float* d_scores, char* ws, const Workspace& L, cudaStream_t st);
 bool tc_bwd_available();
+int run_grad_gemm(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
+                  const Workspace& L, cudaStream_t st);
+extern void* g_trace_buffer;
 
 Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc) {
   Workspace L{};
@@ -79,6 +82,11 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   L.dth = take(nt * d * 4);
   L.dgv = take(nv * R * 4);
   L.dgt = take(nt * W * 4);
+  {
+    const size_t units = (size_t)Bv * ((Bt + 3) / 4);
+    L.pa = take(tc ? units * R * 128 * 2 : 0);
+    L.pb = take(tc ? units * R * 128 * 2 : 0);
+  }
   // generic kernels (also the backward fallback of the tcgen05 forward): per-CTA scratch
   long long pairs = (long long)Bv * Bt;
   int sms = 148;
@@ -148,6 +156,9 @@ int dvlp_last_cuda_error(void) { return g_last_cuda_error; }
 int dvlp_rw_tcgen05_supported(int R, int W, int d) { return tc_supported(R, W, d) ? 1 : 0; }
 void dvlp_set_default_impl(int impl) { g_default_impl.store(impl); }
 uint64_t dvlp_launch_count(void) { return g_launches.load(); }
+
+/* debug only (not in the public header): device buffer of 5*32*16 int64 clock stamps, see pair_tc_bwd.cu */
+void dvlp_debug_set_trace(void* dev_buffer) { g_trace_buffer = dev_buffer; }
 
 void dvlp_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 
@@ -224,7 +235,7 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   // zero the accumulators (one contiguous range: dvh .. dgt)
-  DVLP_CUDA_OK(cudaMemsetAsync(ws + L.dvh, 0, L.scratch - L.dvh, st));
+  DVLP_CUDA_OK(cudaMemsetAsync(ws + L.dvh, 0, L.pa - L.dvh, st));
   int prescaled = 0;
   {
   ProfScope p(kProfBwd, st);
@@ -232,6 +243,7 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
     if ((rc = run_pair_tc_bwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, d_scores, ws, L, st))) return rc;
+    if ((rc = run_grad_gemm(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
     prescaled = 1;
   } else {
     PairArgs a{};

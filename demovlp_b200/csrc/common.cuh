@@ -85,6 +85,7 @@ struct Workspace {
   // backward accumulators
   size_t dvh, dth;           // fp32 (Bv,R,d), (Bt,W,d)
   size_t dgv, dgt;           // fp32 (Bv,R,R), (Bt,W,W)
+  size_t pa, pb;             // tcgen05 backward: bf16 P tiles (Bv * ceil(Bt/4), R, 128) spilled for grad_gemm.cu
   size_t scratch;            // generic kernels: per-CTA pair scratch
   size_t total;
   int n_cta;                 // generic kernels: persistent grid size

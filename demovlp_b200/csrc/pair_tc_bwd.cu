@@ -7,7 +7,13 @@
 //   S1 = T V^T, S2 = V T^T                      raw similarities, both orientations      (as forward)
 //   Y1 = U1 G^V,  Y2 = U2 G^T                   Gram-form denominators                   (as forward)
 //   dG^V += UD1^T U1,  dG^T += UD2^T U2         gradient of the Gram matrices  (UD = U * dD per query)
-//   dV'  += (P1^T + P2) T,   dT' += (P1^T + P2)^T V     P = dS * alpha_r * beta_w  (bf16 operands)
+//
+// The two d-wide gradient products  dV' = sum_j (P1^T + P2) T_j  and  dT' = sum_i (P1^T + P2)^T V_i
+// (P = dS * alpha_r * beta_w, bf16) are NOT formed here: per-tile accumulators would have to be flushed
+// with fp32 L2 atomics (250 KB per tile; measured 6 TB/s chip-wide at best, tools/ubench/red_bw.cu),
+// which bounded the first version of this kernel.  Instead the two bf16 P tiles (2 x 20 KB) leave
+// through TMA stores and grad_gemm.cu contracts them against T / V as dense, accumulator-stationary
+// tcgen05 GEMMs (no atomics, 10x less traffic).
 //
 // Operand staging (all [region rows][word columns], 128-byte swizzle): U1^T / UD1^T written by group A
 // (thread = word) with transposed 16-bit stores, U2 / UD2 written row-wise by group B (thread = region);
@@ -15,7 +21,7 @@
 // K-major operand in one product and as an MN-major operand in the other (UMMA descriptors).
 // The cross-row sums of the l2-norm backward (sum over the query axis = over THREADS in each group's
 // orientation) are done with warp-shuffle transpose-reductions.
-// Gradient tiles are flushed from TMEM with vector red.global adds (accumulators live in L2).
+// The small Gram gradients dG^V / dG^T are flushed from TMEM with vector red.global adds.
 //
 // Warp roles (512 threads, 4 warpgroups, registers re-split with setmaxnreg):
 //   WG0: warp 0 TMA producer, warp 1 MMA issuer;  WG1: group A;  WG2 / WG3: group B for texts 0,1 / 2,3 of the tile.
@@ -26,6 +32,8 @@
 
 namespace dvlp {
 using namespace ptx;
+
+void* g_trace_buffer = nullptr;   // set through dvlp_debug_set_trace (tools/trace_tiles.py)
 
 namespace tcb {
 constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128, kThreads = 512;
@@ -59,11 +67,11 @@ struct Lay {
   static_assert(kAlloc <= 232448, "shared memory budget");
 };
 
-enum Bar { V_FULL = 0, T_FULL, GT_FULL, T_EMPTY, S_DONE, U_READY, Y_DONE, UD_READY, DG_DONE, P_READY, GRAD_DONE,
-           SCRATCH_FREE, kNumBars };
+enum Bar { V_FULL = 0, T_FULL, GT_FULL, T_EMPTY, S_DONE, U_READY, Y_DONE, UD_READY, DG_DONE, P_READY, P_STORED,
+           kNumBars };
 
 // TMEM columns (everything is per-tile scratch, reused phase by phase)
-constexpr uint32_t cS1 = 0, cS2 = 128, cY2 = 256, cDGT = 384, cDV = 0, cDT = 256;
+constexpr uint32_t cS1 = 0, cS2 = 128, cY2 = 256, cDGT = 384;
 
 struct Args {
   int Bv, Bt, tiles_per_video;
@@ -71,8 +79,16 @@ struct Args {
   const float *alpha, *beta, *m2v, *m2t, *d_scores;
   float lam, lam2;
   int focal;
-  float *dvh, *dth, *dgv, *dgt;
+  float *dgv, *dgt;
+  long long* trace;   // debug: per-phase clock64 stamps of CTA 0 (tools/trace_tiles.py), NULL in production
 };
+// trace slot layout: [role 0..4][tile 0..31][event 0..15]
+#define TR(role, ev)                                                                        \
+  do {                                                                                      \
+    if (a.trace && blockIdx.x == 0 && lane == 0 && k < 32) a.trace[((role) * 32 + k) * 16 + (ev)] = clock64(); \
+  } while (0)
+#define TRA(ev) do { if (warp == 4) TR(2, ev); } while (0)
+#define TRB(ev) do { if (q == 0) TR(3 + hb, ev); } while (0)
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -116,7 +132,8 @@ __device__ __forceinline__ float lanes_to_columns16(float (&v)[16], int lane) {
 template <int R>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapT,
-              const __grid_constant__ CUtensorMap mapGV, const __grid_constant__ CUtensorMap mapGT, Args a) {
+              const __grid_constant__ CUtensorMap mapGV, const __grid_constant__ CUtensorMap mapGT,
+              const __grid_constant__ CUtensorMap mapPa, const __grid_constant__ CUtensorMap mapPb, Args a) {
   using L = Lay<R>;
   static_assert(R % 16 == 0 && R >= 16 && R <= 128, "R must be a multiple of 16 in [16,128]");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -141,9 +158,10 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapV); prefetch_tmap(&mapT); prefetch_tmap(&mapGV); prefetch_tmap(&mapGT);
+    prefetch_tmap(&mapPa); prefetch_tmap(&mapPb);
     for (int i = 0; i < kNumBars; ++i) {
       uint32_t cnt = 1;
-      if (i == U_READY || i == UD_READY || i == P_READY || i == SCRATCH_FREE) cnt = 384;
+      if (i == U_READY || i == UD_READY || i == P_READY) cnt = 384;
       mbar_init(bar(i), cnt);
     }
     fence_mbar_init();
@@ -167,7 +185,11 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       // =============================== TMA producer ===============================
       for (int k = 0; k < n_tiles; ++k) {
         const int i = video_of(k), jt = tile_of(k);
-        if (k > 0) mbar_wait(bar(T_EMPTY), (k - 1) & 1);   // gradient GEMMs of tile k-1 have read T and V
+        if (k > 0) mbar_wait(bar(T_EMPTY), (k - 1) & 1);   // S GEMMs of tile k-1 have read T
+        mbar_arrive_expect_tx(bar(T_FULL), 4 * kTileBytes);
+        for (int c = 0; c < 4; ++c) tma_load_2d(sbase + L::T + c * kTileBytes, &mapT, c * 64, jt * kRows, bar(T_FULL));
+        // everything else is still read by the groups / the Y GEMMs until tile k-1 has written its P tiles
+        if (k > 0) mbar_wait(bar(P_READY), (k - 1) & 1);
         if (is_switch(k)) {
           mbar_arrive_expect_tx(bar(V_FULL), 6 * L::kVChunk + 2 * R * 4);
           for (int c = 0; c < 4; ++c) tma_load_2d(sbase + L::V + c * L::kVChunk, &mapV, c * 64, i * R, bar(V_FULL));
@@ -175,8 +197,6 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           bulk_load(sbase + L::ALPHA, a.alpha + (size_t)i * R, R * 4, bar(V_FULL));
           bulk_load(sbase + L::M2V, a.m2v + (size_t)i * R, R * 4, bar(V_FULL));
         }
-        mbar_arrive_expect_tx(bar(T_FULL), 4 * kTileBytes);
-        for (int c = 0; c < 4; ++c) tma_load_2d(sbase + L::T + c * kTileBytes, &mapT, c * 64, jt * kRows, bar(T_FULL));
         mbar_arrive_expect_tx(bar(GT_FULL), kTileBytes + 1024);
         tma_load_2d(sbase + L::GT, &mapGT, 0, jt * kRows, bar(GT_FULL));
         bulk_load(sbase + L::BETA, a.beta + (size_t)jt * kRows, 512, bar(GT_FULL));
@@ -184,97 +204,99 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       }
     } else if (warp == 1) {
       // ================================ MMA issuer ================================
+      // Descriptors are loop invariant: their words are built once and every MMA only adds a constant to
+      // the 14-bit address field (a single thread issuing dependent 64-bit arithmetic per MMA cost ~130
+      // cycles per instruction in the first version of this kernel).
       constexpr uint32_t idS1 = idesc_bf16(128, R), idS2 = idesc_bf16(128, 128), idY2 = idesc_bf16(128, 32);
       constexpr uint32_t idY1 = idesc_bf16(128, R, 1, 0);          // A = U1 (MN-major view of U1^T)
       constexpr uint32_t idDGT = idesc_bf16(128, 128, 1, 1);       // UD2^T U2: both MN-major
-      constexpr uint32_t idDV = idesc_bf16(128, 256, 0, 1);        // P (K-major) x T (MN-major)
-      constexpr uint32_t idDT = idesc_bf16(128, 256, 1, 1);        // P^T (MN-major) x V (MN-major)
       constexpr uint32_t CH = L::kVChunk;                          // chunk stride of R-row buffers
+      const uint32_t hiK = desc_hi(1024);                          // K-major tiles: 8-row groups 1024 B apart
+      const uint32_t loT = desc_lo(sbase + L::T), loV = desc_lo(sbase + L::V), loGV = desc_lo(sbase + L::GV);
+      const uint32_t loGT = desc_lo(sbase + L::GT);
+      const uint32_t loA1 = desc_lo(sbase + L::A1), loA2 = desc_lo(sbase + L::A2);
+      const uint32_t loB1 = desc_lo(sbase + L::B1), loB2 = desc_lo(sbase + L::B2);
+      const uint32_t loA1m = desc_lo(sbase + L::A1, CH), loB1m = desc_lo(sbase + L::B1, CH);   // MN-major views
+      const uint32_t loB2m = desc_lo(sbase + L::B2, CH);
       int vloads = 0;
       for (int k = 0; k < n_tiles; ++k) {
         const uint32_t ph = k & 1;
         if (is_switch(k)) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
         mbar_wait(bar(T_FULL), ph);
-        if (k > 0) mbar_wait(bar(SCRATCH_FREE), (k - 1) & 1);
         tc_fence_after();
+        TR(1, 0);
         if (lane == 0) {
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < 16; ++ks) {
-            const uint32_t off = (ks >> 2), sub = (ks & 3) * 32;
-            mma_bf16(tmem + cS1, smem_desc_sw128(sbase + L::T + off * kTileBytes + sub, 1024),
-                     smem_desc_sw128(sbase + L::V + off * CH + sub, 1024), idS1, ks != 0);
+            const uint32_t oT = ((ks >> 2) * kTileBytes + (ks & 3) * 32) >> 4, oV = ((ks >> 2) * CH + (ks & 3) * 32) >> 4;
+            mma_bf16_w(tmem + cS1, loT + oT, hiK, loV + oV, hiK, idS1, ks != 0);
           }
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < 16; ++ks) {
-            const uint32_t off = (ks >> 2), sub = (ks & 3) * 32;
-            mma_bf16(tmem + cS2, smem_desc_sw128(sbase + L::V + off * CH + sub, 1024),
-                     smem_desc_sw128(sbase + L::T + off * kTileBytes + sub, 1024), idS2, ks != 0);
+            const uint32_t oT = ((ks >> 2) * kTileBytes + (ks & 3) * 32) >> 4, oV = ((ks >> 2) * CH + (ks & 3) * 32) >> 4;
+            mma_bf16_w(tmem + cS2, loV + oV, hiK, loT + oT, hiK, idS2, ks != 0);
           }
           tc_commit(bar(S_DONE));
+          tc_commit(bar(T_EMPTY));
         }
         __syncwarp();
+        TR(1, 1);
         // ---- Y1 = U1 G^V (A: MN-major from U1^T), Y2 = U2 G^T
         mbar_wait(bar(U_READY), ph);
         mbar_wait(bar(GT_FULL), ph);
         tc_fence_after();
+        TR(1, 2);
         if (lane == 0) {
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < R / 16; ++ks)
-            mma_bf16(tmem + cS1, smem_desc_sw128(sbase + L::A1 + ks * 2048, 1024, CH),
-                     smem_desc_sw128(sbase + L::GV + (ks >> 2) * CH + (ks & 3) * 32, 1024), idY1, ks != 0);
-#pragma unroll 1
+            mma_bf16_w(tmem + cS1, loA1m + ((ks * 2048) >> 4), hiK, loGV + (((ks >> 2) * CH + (ks & 3) * 32) >> 4), hiK,
+                       idY1, ks != 0);
+#pragma unroll
           for (int t = 0; t < kTPT; ++t)
-#pragma unroll 1
+#pragma unroll
             for (int s = 0; s < 2; ++s)
-              mma_bf16(tmem + cY2 + t * 32,
-                       smem_desc_sw128(sbase + L::B1 + (t >> 1) * CH + (t & 1) * 64 + s * 32, 1024),
-                       smem_desc_sw128(sbase + L::GT + t * 4096 + s * 32, 1024), idY2, s != 0);
+              mma_bf16_w(tmem + cY2 + t * 32, loB1 + (((t >> 1) * CH + (t & 1) * 64 + s * 32) >> 4), hiK,
+                         loGT + ((t * 4096 + s * 32) >> 4), hiK, idY2, s != 0);
           tc_commit(bar(Y_DONE));
         }
         __syncwarp();
+        TR(1, 3);
         // ---- dG^V = UD1^T(K-major rows=regions) x U1^T(K-major rows=regions), K = 128 words
         //      dG^T = UD2^T U2 : A, B MN-major (M, N = words), K = regions
         mbar_wait(bar(UD_READY), ph);
         tc_fence_after();
+        TR(1, 4);
         if (lane == 0) {
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t o = (ks >> 2) * CH + (ks & 3) * 32;
-            mma_bf16(tmem + cS1, smem_desc_sw128(sbase + L::A2 + o, 1024), smem_desc_sw128(sbase + L::A1 + o, 1024),
-                     idS1, ks != 0);
+            const uint32_t o = ((ks >> 2) * CH + (ks & 3) * 32) >> 4;
+            mma_bf16_w(tmem + cS1, loA2 + o, hiK, loA1 + o, hiK, idS1, ks != 0);
           }
-#pragma unroll 1
+#pragma unroll
           for (int ks = 0; ks < R / 16; ++ks)
-            mma_bf16(tmem + cDGT, smem_desc_sw128(sbase + L::B2 + ks * 2048, 1024, CH),
-                     smem_desc_sw128(sbase + L::B1 + ks * 2048, 1024, CH), idDGT, ks != 0);
+            mma_bf16_w(tmem + cDGT, loB2m + ((ks * 2048) >> 4), hiK, loB1m + ((ks * 2048) >> 4), hiK, idDGT, ks != 0);
           tc_commit(bar(DG_DONE));
         }
         __syncwarp();
-        // ---- dV' = (P1^T + P2) T  and  dT' = (P1^T + P2)^T V
+        TR(1, 5);
+        // ---- the two P tiles of this unit leave through TMA stores (grad_gemm.cu contracts them)
         mbar_wait(bar(P_READY), ph);
-        tc_fence_after();
+        TR(1, 6);
         if (lane == 0) {
-#pragma unroll 1
+          const int row = (int)((u0 + k) * R);
+#pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const uint32_t P = sbase + (c == 0 ? L::A1 : L::B1);
-#pragma unroll 1
-            for (int ks = 0; ks < 8; ++ks)
-              mma_bf16(tmem + cDV, smem_desc_sw128(P + (ks >> 2) * CH + (ks & 3) * 32, 1024),
-                       smem_desc_sw128(sbase + L::T + ks * 2048, 1024, kTileBytes), idDV, (c | ks) != 0);
+            tma_store_2d(&mapPa, sbase + L::A1 + c * CH, c * 64, row);
+            tma_store_2d(&mapPb, sbase + L::B1 + c * CH, c * 64, row);
           }
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t P = sbase + (c == 0 ? L::A1 : L::B1);
-#pragma unroll 1
-            for (int ks = 0; ks < R / 16; ++ks)
-              mma_bf16(tmem + cDT, smem_desc_sw128(P + ks * 2048, 1024, CH),
-                       smem_desc_sw128(sbase + L::V + ks * 2048, 1024, CH), idDT, (c | ks) != 0);
-          }
-          tc_commit(bar(GRAD_DONE));
-          tc_commit(bar(T_EMPTY));
+          bulk_commit();
+          bulk_wait_read0();                 // the staging tiles may be overwritten (next tile's U)
+          mbar_arrive(bar(P_STORED));
         }
         __syncwarp();
+        TR(1, 7);
       }
+      if (lane == 0) bulk_wait_all();        // global writes complete before the CTA retires
     }
   } else if (warp < 8) {
     // ================== group A: i2t direction, thread = word row ==================
@@ -291,10 +313,12 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     for (int k = 0; k < n_tiles; ++k) {
       const uint32_t ph = k & 1;
       const int i = video_of(k), jt = tile_of(k), j = jt * kTPT + q;
+      TRA(0);
       if (is_switch(k)) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
       mbar_wait(bar(GT_FULL), ph);
       mbar_wait(bar(S_DONE), ph);
       tc_fence_after();
+      TRA(1);
       const float beta_m = s_beta[m];
       const float g = j < a.Bt ? a.d_scores[(size_t)i * a.Bt + j] : 0.f;
       float S[R], Y[R];
@@ -314,7 +338,10 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         for (int h = 0; h < 4; ++h) { float l = leaky(S[r + h]); acc4[h] = fmaf(l, l, acc4[h]); }
       }
       s_invnB[m] = 1.f / (sqrtf((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + kEps);
+      TRA(2);
       named_bar_sync(1, kGroup);
+      TRA(3);
+      if (k > 0) mbar_wait(bar(P_STORED), (k - 1) & 1);   // TMA stores of tile k-1 have read A1 / B1
       // forward pass 2 (e kept in Y[] until the focal threshold is known)
       acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.f;
 #pragma unroll
@@ -342,9 +369,11 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       const float num = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
       fence_proxy_async();
       mbar_arrive(bar(U_READY));
+      TRA(4);
       // ---- denominators and per-word scalars
       mbar_wait(bar(Y_DONE), ph);
       tc_fence_after();
+      TRA(5);
       {
         uint32_t* raw = reinterpret_cast<uint32_t*>(Y);
 #pragma unroll
@@ -378,6 +407,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar(UD_READY));
+      TRA(6);
       // ---- t_r = sum over this text's words of A dA  (l2-norm backward, model/loss.py:238)
       {
         float tot[(R + 31) / 32];
@@ -405,7 +435,9 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         if ((R % 32) && lane < 16) s_tA[q * R + (R / 32) * 32 + lane] = tot[R / 32];
         __syncwarp();
       }
+      TRA(7);
       mbar_wait(bar(DG_DONE), ph);                     // U1^T / UD1^T consumed: A1 may take P1^T
+      TRA(8);
       // pass B3: dS = (dA - A t) / n * leaky'(S) + c1 u ;  P = dS alpha_r beta_w
 #pragma unroll
       for (int r = 0; r < R; r += 4) {
@@ -439,25 +471,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar(P_READY));
-      // ---- flush dT' rows of this word
-      mbar_wait(bar(GRAD_DONE), ph);
-      tc_fence_after();
-      {
-        float* dst = a.dth + ((size_t)jt * kRows + m) * kD;
-#pragma unroll 1
-        for (int c = 0; c < kD; c += 32) {
-          float v[32];
-          tmem_ld16(tmem + cDT + lane_off + c, reinterpret_cast<uint32_t*>(v));
-          tmem_ld16(tmem + cDT + lane_off + c + 16, reinterpret_cast<uint32_t*>(v) + 16);
-          tmem_ld_wait();
-          if (j < a.Bt) {
-#pragma unroll
-            for (int x = 0; x < 32; x += 4) red_add_v4(dst + c + x, v[x], v[x + 1], v[x + 2], v[x + 3]);
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar(SCRATCH_FREE));
+      TRA(9);
     }
   } else {
     // ================= group B: t2i direction, thread = region row =================
@@ -478,10 +492,12 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     for (int k = 0; k < n_tiles; ++k) {
       const uint32_t ph = k & 1;
       const int i = video_of(k), jt = tile_of(k);
+      TRB(0);
       if (is_switch(k)) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
       mbar_wait(bar(GT_FULL), ph);
       mbar_wait(bar(S_DONE), ph);
       tc_fence_after();
+      TRB(1);
       const float alpha_r = active ? s_alpha[r] : 0.f;
       float num[2], c1v[2], kapv[2];
       if (warp_active) {
@@ -504,7 +520,10 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           if (active) s_invnA[t * R + r] = 1.f / (sqrtf((s4[0] + s4[1]) + (s4[2] + s4[3])) + kEps);
         }
       }
+      TRB(2);
       named_bar_sync(1, kGroup);
+      TRB(3);
+      if (k > 0) mbar_wait(bar(P_STORED), (k - 1) & 1);   // TMA stores of tile k-1 have read A1 / B1
       if (warp_active) {
 #pragma unroll
         for (int tt = 0; tt < 2; ++tt) {
@@ -546,9 +565,11 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       }
       fence_proxy_async();
       mbar_arrive(bar(U_READY));
+      TRB(4);
       // ---- loop A: denominators, per-(region, text) scalars, UD2 = u dD
       mbar_wait(bar(Y_DONE), ph);
       tc_fence_after();
+      TRB(5);
       if (warp_active) {
 #pragma unroll
         for (int tt = 0; tt < 2; ++tt) {
@@ -590,6 +611,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       }
       fence_proxy_async();
       mbar_arrive(bar(UD_READY));
+      TRB(6);
       // ---- loop B: per text, dA, the cross-region sum t_w = sum_r A dA, dS, P2
 #pragma unroll 1
       for (int tt = 0; tt < 2; ++tt) {
@@ -648,6 +670,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         }
       }
       // dG^V rows of this region
+      TRB(7);
       tc_fence_after();
       if (warp_active) {
         float* dst = a.dgv + ((size_t)i * R + r) * R;
@@ -665,25 +688,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar(P_READY));
-      // ---- flush dV' rows of this region
-      mbar_wait(bar(GRAD_DONE), ph);
-      tc_fence_after();
-      if (warp_active) {
-        float* dst = a.dvh + ((size_t)i * R + r) * kD;
-#pragma unroll 1
-        for (int c = hb * 32; c < kD; c += 64) {        // the two halves take alternate 32-column chunks
-          float v[32];
-          tmem_ld16(tmem + cDV + lane_off + c, reinterpret_cast<uint32_t*>(v));
-          tmem_ld16(tmem + cDV + lane_off + c + 16, reinterpret_cast<uint32_t*>(v) + 16);
-          tmem_ld_wait();
-          if (active) {
-#pragma unroll
-            for (int x4 = 0; x4 < 32; x4 += 4) red_add_v4(dst + c + x4, v[x4], v[x4 + 1], v[x4 + 2], v[x4 + 3]);
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar(SCRATCH_FREE));
+      TRB(9);
     }
   }
 
@@ -724,22 +729,25 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 template <int R>
 static int launch_bwd(const void* vb, const void* tb, int Bv, int Bt, float lambda, int focal, const float* d_scores,
                       char* ws, const Workspace& Lw, cudaStream_t st) {
-  CUtensorMap mV, mT, mGV, mGT;
+  CUtensorMap mV, mT, mGV, mGT, mPa, mPb;
   int rc;
-  if ((rc = make_map(&mV, vb, (uint64_t)Bv * R, kD, R))) return rc;
-  if ((rc = make_map(&mT, tb, (uint64_t)Bt * kW, kD, kRows))) return rc;
-  if ((rc = make_map(&mGV, ws + Lw.gvb, (uint64_t)Bv * R, R, R))) return rc;
-  if ((rc = make_map(&mGT, ws + Lw.gtb, (uint64_t)Bt * kW, kW, kRows))) return rc;
   Args a{};
   a.Bv = Bv; a.Bt = Bt;
   a.tiles_per_video = (Bt + kTPT - 1) / kTPT;
   a.total_units = (long long)Bv * a.tiles_per_video;
+  if ((rc = make_map(&mV, vb, (uint64_t)Bv * R, kD, R))) return rc;
+  if ((rc = make_map(&mT, tb, (uint64_t)Bt * kW, kD, kRows))) return rc;
+  if ((rc = make_map(&mGV, ws + Lw.gvb, (uint64_t)Bv * R, R, R))) return rc;
+  if ((rc = make_map(&mGT, ws + Lw.gtb, (uint64_t)Bt * kW, kW, kRows))) return rc;
+  // P spill: [unit][region][128 words] bf16, one R-row box per 64-word half
+  if ((rc = make_map(&mPa, ws + Lw.pa, (uint64_t)a.total_units * R, kRows, R))) return rc;
+  if ((rc = make_map(&mPb, ws + Lw.pb, (uint64_t)a.total_units * R, kRows, R))) return rc;
   a.alpha = (const float*)(ws + Lw.alpha); a.beta = (const float*)(ws + Lw.beta);
   a.m2v = (const float*)(ws + Lw.m2v); a.m2t = (const float*)(ws + Lw.m2t);
   a.d_scores = d_scores;
   a.lam = lambda; a.lam2 = lambda * kLog2e; a.focal = focal;
-  a.dvh = (float*)(ws + Lw.dvh); a.dth = (float*)(ws + Lw.dth);
   a.dgv = (float*)(ws + Lw.dgv); a.dgt = (float*)(ws + Lw.dgt);
+  a.trace = (long long*)g_trace_buffer;
   int dev = 0, sms = 148;
   DVLP_CUDA_OK(cudaGetDevice(&dev));
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -749,7 +757,7 @@ static int launch_bwd(const void* vb, const void* tb, int Bv, int Bt, float lamb
     DVLP_CUDA_OK(cudaFuncSetAttribute(k_pair_tc_bwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<R>::kAlloc));
     attr_set = true;
   }
-  k_pair_tc_bwd<R><<<grid, kThreads, Lay<R>::kAlloc, st>>>(mV, mT, mGV, mGT, a);
+  k_pair_tc_bwd<R><<<grid, kThreads, Lay<R>::kAlloc, st>>>(mV, mT, mGV, mGT, mPa, mPb, a);
   DVLP_LAUNCH_OK();
   return DVLP_OK;
 }
