@@ -38,6 +38,8 @@ int run_prep(const void*, const void*, const float*, const float*, int, int, int
 int run_pair_generic(bool backward, const PairArgs& a, int n_cta, cudaStream_t st);
 int run_grad_finalize(const void*, int, const float*, const float*, const float*, int, int, int, int, float*,
                       cudaStream_t);
+int run_grad_finalize_tc(const void*, const void*, const float*, const float*, const float*, const float*, const float*,
+                         const float*, int, int, int, int, float*, float*, cudaStream_t);
 int run_rwa_loss(const float*, int, int, int, int, float, float*, float*, cudaStream_t);
 int run_normsoftmax(const float*, int, int, float, float*, float*, float*, cudaStream_t);
 int run_sim_fwd(const void*, const void*, int, int, int, float, int, float*, float*, cudaStream_t);
@@ -262,6 +264,10 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   const void* xv = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.vb) : im;
   const void* xt = (tc && in_dtype == DVLP_F32) ? (const void*)(ws + L.tb) : s;
   int xdt = (tc && in_dtype == DVLP_F32) ? DVLP_BF16 : in_dtype;
+  if (prescaled && d == 256 && (R % 16) == 0 && (W % 16) == 0 && R <= 128 && W <= 128)
+    return run_grad_finalize_tc(xv, xt, (const float*)(ws + L.alpha), (const float*)(ws + L.beta),
+                                (const float*)(ws + L.dvh), (const float*)(ws + L.dth), (const float*)(ws + L.dgv),
+                                (const float*)(ws + L.dgt), Bv, Bt, R, W, d_im, d_s, st);
   if ((rc = run_grad_finalize(xv, xdt, (const float*)(ws + L.alpha), (const float*)(ws + L.dvh),
                               (const float*)(ws + L.dgv), Bv, R, d, prescaled, d_im, st)))
     return rc;

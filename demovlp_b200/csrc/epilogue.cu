@@ -5,6 +5,7 @@
 //   g_r   = dXh_r [/ inv_r when the GEMM left an extra inv_r factor] + 2 sum_c dG[r][c] Xh_c
 //   d_x_r = inv_r ( g_r - Xh_r (Xh_r . g_r) )            inv_r = 1/(|x_r| + eps)
 #include "common.cuh"
+#include "mma_sync.cuh"
 
 namespace dvlp {
 
@@ -118,6 +119,112 @@ __global__ void __launch_bounds__(256) k_grad_finalize_tile(const Tin* __restric
       if (r < L && on) d_x[((size_t)item * L + r) * d + k] = iv[r] * (acc[rr] - xh[rr] * dots[rr]);
     }
   }
+}
+
+// tcgen05 path (bf16 rows, d == 256, L % 16 == 0, L <= 128, dX' prescaled by inv_r): one CTA per video / text.
+//   D_r   = dX'_r + sum_c (2 inv_r inv_c dG[r][c]) x_c         (= inv_r g_r;  mma.sync, bf16 operands, fp32 acc)
+//   d_x_r = D_r - inv_r^2 (x_r . D_r) x_r                       (the l2norm backward, model/loss.py:333-338)
+// Warp w owns rows 16w..16w+15 and all 256 columns (128 accumulator registers per thread).
+constexpr int kFinLdX = (256 + 8) * 2;      // bytes
+__global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ t,
+                                                       const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                       const float* __restrict__ dvh, const float* __restrict__ dth,
+                                                       const float* __restrict__ dgv, const float* __restrict__ dgt,
+                                                       int Bv, int R, int W, float* __restrict__ d_im, float* __restrict__ d_s) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  __shared__ float s_inv[128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool text = (int)blockIdx.x >= Bv;
+  const int item = text ? blockIdx.x - Bv : blockIdx.x;
+  const int L = text ? W : R;
+  const __nv_bfloat16* X = (text ? t : v) + (size_t)item * L * 256;
+  const float* inv = (text ? beta : alpha) + (size_t)item * L;
+  const float* dX = (text ? dth : dvh) + (size_t)item * L * 256;
+  const float* dG = (text ? dgt : dgv) + (size_t)item * L * L;
+  float* out = (text ? d_s : d_im) + (size_t)item * L * 256;
+  const int ldA = (L + 8) * 2;
+  uint8_t* xs = fsm;                         // [L][264] bf16 raw rows
+  uint8_t* as = fsm + (size_t)L * kFinLdX;   // [L][L+8] bf16: 2 inv_r inv_c dG[r][c]
+  const uint32_t xb = (uint32_t)__cvta_generic_to_shared(xs), ab = (uint32_t)__cvta_generic_to_shared(as);
+  for (int e = threadIdx.x; e < L; e += blockDim.x) s_inv[e] = inv[e];
+  for (int e = threadIdx.x; e < L * 32; e += blockDim.x) {
+    const int row = e >> 5, ch = e & 31;
+    *reinterpret_cast<uint4*>(xs + row * kFinLdX + ch * 16) = reinterpret_cast<const uint4*>(X)[e];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < L * L / 2; e += blockDim.x) {
+    const int r = (2 * e) / L, c = 2 * e - r * L;
+    const float2 g = *reinterpret_cast<const float2*>(dG + (size_t)r * L + c);
+    const float sr = 2.f * s_inv[r];
+    *reinterpret_cast<__nv_bfloat162*>(as + r * ldA + c * 2) = __floats2bfloat162_rn(g.x * sr * s_inv[c], g.y * sr * s_inv[c + 1]);
+  }
+  __syncthreads();
+  if (warp * 16 >= L) return;
+  const int row0 = warp * 16, g = lane >> 2, tq = lane & 3;
+  float acc[32][4];
+#pragma unroll
+  for (int n = 0; n < 32; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+  for (int k0 = 0; k0 < L; k0 += 16) {
+    uint32_t a[4];
+    mm::load_a(ab, ldA, row0, k0, lane, a);
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) {
+      uint32_t b[4];
+      mm::load_b_kn(xb, kFinLdX, k0, n2 * 16, lane, b);
+      mm::mma_16816(acc[2 * n2], a[0], a[1], a[2], a[3], b[0], b[1]);
+      mm::mma_16816(acc[2 * n2 + 1], a[0], a[1], a[2], a[3], b[2], b[3]);
+    }
+  }
+  // add the prescaled S-path gradient; row dots with the raw row
+  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+  float dot_lo = 0.f, dot_hi = 0.f;
+#pragma unroll
+  for (int n = 0; n < 32; ++n) {
+    const int c = n * 8 + tq * 2;
+    const float2 d_lo = *reinterpret_cast<const float2*>(dX + (size_t)r_lo * 256 + c);
+    const float2 d_hi = *reinterpret_cast<const float2*>(dX + (size_t)r_hi * 256 + c);
+    acc[n][0] += d_lo.x; acc[n][1] += d_lo.y; acc[n][2] += d_hi.x; acc[n][3] += d_hi.y;
+    const uint32_t x_lo = *reinterpret_cast<const uint32_t*>(xs + r_lo * kFinLdX + c * 2);
+    const uint32_t x_hi = *reinterpret_cast<const uint32_t*>(xs + r_hi * kFinLdX + c * 2);
+    dot_lo = fmaf(__uint_as_float(x_lo << 16), acc[n][0], dot_lo);
+    dot_lo = fmaf(__uint_as_float(x_lo & 0xffff0000u), acc[n][1], dot_lo);
+    dot_hi = fmaf(__uint_as_float(x_hi << 16), acc[n][2], dot_hi);
+    dot_hi = fmaf(__uint_as_float(x_hi & 0xffff0000u), acc[n][3], dot_hi);
+  }
+  dot_lo += __shfl_xor_sync(0xffffffffu, dot_lo, 1); dot_lo += __shfl_xor_sync(0xffffffffu, dot_lo, 2);
+  dot_hi += __shfl_xor_sync(0xffffffffu, dot_hi, 1); dot_hi += __shfl_xor_sync(0xffffffffu, dot_hi, 2);
+  const float k_lo = s_inv[r_lo] * s_inv[r_lo] * dot_lo, k_hi = s_inv[r_hi] * s_inv[r_hi] * dot_hi;
+#pragma unroll
+  for (int n = 0; n < 32; ++n) {
+    const int c = n * 8 + tq * 2;
+    const uint32_t x_lo = *reinterpret_cast<const uint32_t*>(xs + r_lo * kFinLdX + c * 2);
+    const uint32_t x_hi = *reinterpret_cast<const uint32_t*>(xs + r_hi * kFinLdX + c * 2);
+    float2 o_lo, o_hi;
+    o_lo.x = fmaf(-k_lo, __uint_as_float(x_lo << 16), acc[n][0]);
+    o_lo.y = fmaf(-k_lo, __uint_as_float(x_lo & 0xffff0000u), acc[n][1]);
+    o_hi.x = fmaf(-k_hi, __uint_as_float(x_hi << 16), acc[n][2]);
+    o_hi.y = fmaf(-k_hi, __uint_as_float(x_hi & 0xffff0000u), acc[n][3]);
+    *reinterpret_cast<float2*>(out + (size_t)r_lo * 256 + c) = o_lo;
+    *reinterpret_cast<float2*>(out + (size_t)r_hi * 256 + c) = o_hi;
+  }
+}
+
+// both sides in one launch (tcgen05 path)
+int run_grad_finalize_tc(const void* v, const void* t, const float* alpha, const float* beta, const float* dvh,
+                         const float* dth, const float* dgv, const float* dgt, int Bv, int Bt, int R, int W,
+                         float* d_im, float* d_s, cudaStream_t st) {
+  const int Lmax = R > W ? R : W;
+  const size_t smem = (size_t)Lmax * kFinLdX + (size_t)Lmax * (Lmax + 8) * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_finalize_item, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      128 * kFinLdX + 128 * 136 * 2));
+    attr_set = true;
+  }
+  k_finalize_item<<<Bv + Bt, 256, smem, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)t, alpha, beta, dvh, dth,
+                                              dgv, dgt, Bv, R, W, d_im, d_s);
+  DVLP_LAUNCH_OK();
+  return DVLP_OK;
 }
 
 int run_grad_finalize(const void* x, int in_dtype, const float* inv, const float* dxh, const float* dG, int items,

@@ -6,6 +6,7 @@
 // lets the kernels evaluate |weighted context|^2 = q^T G q without forming the (.., d)-wide
 // weighted-context tensor of model/loss.py:262-269 ("Gram form").
 #include "common.cuh"
+#include "mma_sync.cuh"
 
 namespace dvlp {
 
@@ -127,6 +128,102 @@ __global__ void __launch_bounds__(256) k_gram_tile(const __nv_bfloat16* __restri
   }
 }
 
+
+// Fused per-item prologue of the tcgen05 path (bf16 rows, d == 256, L % 16 == 0, L <= 128): one CTA per
+// video / text stages the item's rows in shared memory once and produces the inverse row norms, both mask
+// terms and the bf16 Gram matrix G = Xh Xh^T.  The Gram product runs on mma.sync with the RAW bf16 rows
+// (exact products, fp32 accumulate) and is scaled by inv_a inv_b afterwards, like the pair kernels do for S.
+// Block Bv + Bt (if launched) zeroes the padded tail of the text-side vectors.
+constexpr int kPrepLd = (256 + 8) * 2;     // shared-memory row stride in bytes: conflict-free ldmatrix
+__global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ t,
+                                                   const float* __restrict__ vmask, const float* __restrict__ tmask,
+                                                   int Bv, int Bt, int R, int W, float lambda,
+                                                   float* __restrict__ alpha, float* __restrict__ beta,
+                                                   float* __restrict__ mterm_v, float* __restrict__ mterm_t,
+                                                   float* __restrict__ m2v, float* __restrict__ m2t,
+                                                   __nv_bfloat16* __restrict__ gvb, __nv_bfloat16* __restrict__ gtb,
+                                                   int pad_from, int pad_to) {
+  extern __shared__ __align__(16) uint8_t psm[];
+  __shared__ float s_inv[128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x == Bv + Bt) {            // padded tail of beta / m2t (whole 128-row tiles are bulk-copied)
+    for (int e = pad_from + threadIdx.x; e < pad_to; e += blockDim.x) { beta[e] = 0.f; m2t[e] = 0.f; }
+    return;
+  }
+  const bool text = (int)blockIdx.x >= Bv;
+  const int item = text ? blockIdx.x - Bv : blockIdx.x;
+  const int L = text ? W : R;
+  const __nv_bfloat16* X = (text ? t : v) + (size_t)item * L * 256;
+  const float* mask = (text ? tmask : vmask) + (size_t)item * L;
+  float* inv_out = (text ? beta : alpha) + (size_t)item * L;
+  float* mt = (text ? mterm_t : mterm_v) + (size_t)item * L;
+  float* m2 = (text ? m2t : m2v) + (size_t)item * L;
+  __nv_bfloat16* G = (text ? gtb : gvb) + (size_t)item * L * L;
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(psm);
+  // stage rows (16-byte chunks: 32 per row)
+  for (int e = threadIdx.x; e < L * 32; e += blockDim.x) {
+    const int row = e >> 5, ch = e & 31;
+    const uint4 val = reinterpret_cast<const uint4*>(X)[e];
+    *reinterpret_cast<uint4*>(psm + row * kPrepLd + ch * 16) = val;
+  }
+  __syncthreads();
+  // inverse norms: one warp per row, 8 elements per lane
+  for (int row = warp; row < L; row += 8) {
+    const uint4 val = *reinterpret_cast<const uint4*>(psm + row * kPrepLd + lane * 16);
+    const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
+    float ss = 0.f;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float lo = __uint_as_float(w4[h] << 16), hi = __uint_as_float(w4[h] & 0xffff0000u);
+      ss = fmaf(lo, lo, ss);
+      ss = fmaf(hi, hi, ss);
+    }
+    ss = warp_sum(ss);
+    const float a = 1.f / (sqrtf(ss) + kEps);
+    if (lane == 0) { s_inv[row] = a; inv_out[row] = a; }
+  }
+  // mask terms (warp 7; see k_mask_terms)
+  if (warp == 7) {
+    float mx = -INFINITY;
+    for (int c = lane; c < L; c += 32) mx = fmaxf(mx, mask[c]);
+    mx = warp_max(mx);
+    for (int c = lane; c < L; c += 32) {
+      const float val = lambda * (mask[c] - mx);
+      mt[c] = val;
+      m2[c] = (val - lambda) * kLog2e;
+    }
+  }
+  __syncthreads();
+  // Gram: 16 x 16 output tiles, upper triangle computed and mirrored
+  const int nt = L >> 4;
+  for (int tile = warp; tile < nt * nt; tile += 8) {
+    const int ti = tile / nt, tj = tile - ti * nt;
+    if (tj < ti) continue;
+    float acc[2][4] = {};
+#pragma unroll 4
+    for (int k0 = 0; k0 < 256; k0 += 16) {
+      uint32_t a[4], b[4];
+      mm::load_a(sb, kPrepLd, ti * 16, k0, lane, a);
+      mm::load_b_nk(sb, kPrepLd, tj * 16, k0, lane, b);
+      mm::mma_16816(acc[0], a[0], a[1], a[2], a[3], b[0], b[1]);
+      mm::mma_16816(acc[1], a[0], a[1], a[2], a[3], b[2], b[3]);
+    }
+    const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = ti * 16 + g + half * 8, c = tj * 16 + h * 8 + tq * 2;
+        const float x0 = acc[h][half * 2] * s_inv[r] * s_inv[c], x1 = acc[h][half * 2 + 1] * s_inv[r] * s_inv[c + 1];
+        *reinterpret_cast<__nv_bfloat162*>(G + (size_t)r * L + c) = __floats2bfloat162_rn(x0, x1);
+        if (tj != ti) {
+          G[(size_t)c * L + r] = __float2bfloat16(x0);
+          G[(size_t)(c + 1) * L + r] = __float2bfloat16(x1);
+        }
+      }
+  }
+}
+
 template <typename Tin>
 static int prep_side(const Tin* x, const float* mask, int items, int L, int d, float lambda, float* inv,
                      float* mterm, float* mterm2, float* xh, float* G, __nv_bfloat16* Gb, cudaStream_t st) {
@@ -173,9 +270,10 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
   }
   const __nv_bfloat16* vb = (const __nv_bfloat16*)im;
   const __nv_bfloat16* tb = (const __nv_bfloat16*)s;
-  {
-    // text-side vectors are read in whole 128-row tiles: keep the padded tail finite
-    const size_t nt_pad = ((size_t)Bt * W + 127) / 128 * 128;
+  // text-side vectors are read in whole 128-row tiles: keep the padded tail finite
+  const size_t nt_pad = ((size_t)Bt * W + 127) / 128 * 128;
+  const bool fused = !full && d == 256 && (R % 16) == 0 && (W % 16) == 0 && R <= 128 && W <= 128;
+  if (!fused) {
     DVLP_CUDA_OK(cudaMemsetAsync(ws + L.beta, 0, nt_pad * 4, st));
     DVLP_CUDA_OK(cudaMemsetAsync(ws + L.m2t, 0, nt_pad * 4, st));
   }
@@ -187,6 +285,21 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
     DVLP_LAUNCH_OK();
     vb = (const __nv_bfloat16*)(ws + L.vb);
     tb = (const __nv_bfloat16*)(ws + L.tb);
+  }
+  if (fused) {
+    const int Lmax = R > W ? R : W;
+    const size_t smem = (size_t)Lmax * kPrepLd;
+    static bool attr_set = false;
+    if (!attr_set) {
+      DVLP_CUDA_OK(cudaFuncSetAttribute(k_prep_item, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kPrepLd));
+      attr_set = true;
+    }
+    const bool pad = nt_pad > (size_t)Bt * W;
+    k_prep_item<<<Bv + Bt + (pad ? 1 : 0), 256, smem, st>>>(
+        vb, tb, im_mask, s_mask, Bv, Bt, R, W, lambda, alpha, beta, mv, mt, (float*)(ws + L.m2v), (float*)(ws + L.m2t),
+        (__nv_bfloat16*)(ws + L.gvb), (__nv_bfloat16*)(ws + L.gtb), Bt * W, (int)nt_pad);
+    DVLP_LAUNCH_OK();
+    return DVLP_OK;
   }
   // lean tcgen05 prologue: inverse norms, mask terms (natural + log2 domain), bf16 Gram.  The fp32
   // normalised rows / fp32 Gram of the generic kernels are produced only when `full` is set

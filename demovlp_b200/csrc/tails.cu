@@ -144,10 +144,12 @@ __global__ void __launch_bounds__(1024) k_sim_fwd(const T* __restrict__ a, const
   if (i < N && j < M) out[(size_t)i * M + j] = acc * ia[i] * ib[j];
 }
 
-constexpr int kSimRB = 2;   // rows of `a` per CTA (small: the matrices are small, parallelism matters)
+constexpr int kSimRB = 4;   // rows of `a` per CTA (small: the matrices are small, parallelism matters)
 
 // d_a[i] = inv_i ( g_i - an_i (an_i . g_i) ),  g_i = sum_j w[i][j] bn_j,  w = d_out (TRANS: d_out^T)
 // valid for |a_i| >= eps; a row shorter than eps is scaled by the constant 1/eps instead.
+// The CTA's weights w[i][j] ib[j] are staged in shared memory so the j loop only streams rows of b
+// (8 independent coalesced loads in flight per thread).
 template <typename T, bool TRANS>
 __global__ void __launch_bounds__(256) k_sim_bwd_side(const T* __restrict__ a, const T* __restrict__ b, int N, int M,
                                                       int d, float eps, const float* __restrict__ ia,
@@ -155,25 +157,39 @@ __global__ void __launch_bounds__(256) k_sim_bwd_side(const T* __restrict__ a, c
                                                       float* __restrict__ d_a) {
   // this CTA: RB rows of `a`, all d columns (thread k strides d)
   constexpr int RB = kSimRB;
+  extern __shared__ float wsm[];          // [M][RB]
   __shared__ float red[RB][8];
   const int i0 = blockIdx.x * RB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < RB * M; e += blockDim.x) {
+    const int r = e / M, j = e - r * M, i = i0 + r;
+    float w = 0.f;
+    if (i < N) w = (TRANS ? d_out[(size_t)j * N + i] : d_out[(size_t)i * M + j]) * ib[j];
+    wsm[j * RB + r] = w;
+  }
+  __syncthreads();
   for (int kb = 0; kb < d; kb += blockDim.x) {
     int k = kb + threadIdx.x;
     float g[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) g[r] = 0.f;
     if (k < d) {
-      for (int j = 0; j < M; ++j) {
-        float bn = to_f32(b[(size_t)j * d + k]) * ib[j];
+      int j = 0;
+      for (; j + 8 <= M; j += 8) {
+        float bv[8];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          int i = i0 + r;
-          if (i < N) {
-            float w = TRANS ? d_out[(size_t)j * N + i] : d_out[(size_t)i * M + j];
-            g[r] = fmaf(w, bn, g[r]);
-          }
+        for (int u = 0; u < 8; ++u) bv[u] = to_f32(b[(size_t)(j + u) * d + k]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 w = *reinterpret_cast<const float4*>(wsm + (j + u) * RB);
+          g[0] = fmaf(w.x, bv[u], g[0]); g[1] = fmaf(w.y, bv[u], g[1]);
+          g[2] = fmaf(w.z, bv[u], g[2]); g[3] = fmaf(w.w, bv[u], g[3]);
         }
+      }
+      for (; j < M; ++j) {
+        const float bvv = to_f32(b[(size_t)j * d + k]);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) g[r] = fmaf(wsm[j * RB + r], bvv, g[r]);
       }
     }
     // store g temporarily in d_a, accumulate dot(an, g)
@@ -305,12 +321,19 @@ static int sim_bwd_t(const T* a, const T* b, int N, int M, int d, float eps, con
   DVLP_LAUNCH_OK();
   k_inv_norm_max<T><<<(M + 7) / 8, 256, 0, st>>>(b, M, d, eps, ib);
   DVLP_LAUNCH_OK();
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_sim_bwd_side<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_sim_bwd_side<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if ((size_t)(N > M ? N : M) * kSimRB * 4 > 200 * 1024) return DVLP_ERR_BAD_SHAPE;
   if (d_a) {
-    k_sim_bwd_side<T, false><<<(N + kSimRB - 1) / kSimRB, 256, 0, st>>>(a, b, N, M, d, eps, ia, ib, d_out, d_a);
+    k_sim_bwd_side<T, false><<<(N + kSimRB - 1) / kSimRB, 256, (size_t)M * kSimRB * 4, st>>>(a, b, N, M, d, eps, ia, ib, d_out, d_a);
     DVLP_LAUNCH_OK();
   }
   if (d_b) {
-    k_sim_bwd_side<T, true><<<(M + kSimRB - 1) / kSimRB, 256, 0, st>>>(b, a, M, N, d, eps, ib, ia, d_out, d_b);
+    k_sim_bwd_side<T, true><<<(M + kSimRB - 1) / kSimRB, 256, (size_t)N * kSimRB * 4, st>>>(b, a, M, N, d, eps, ib, ia, d_out, d_b);
     DVLP_LAUNCH_OK();
   }
   return DVLP_OK;
