@@ -88,6 +88,8 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
     const size_t units = (size_t)Bv * ((Bt + 3) / 4);
     L.pa = take(tc ? units * R * 128 * 2 : 0);
     L.pb = take(tc ? units * R * 128 * 2 : 0);
+    L.nrm_a = take(tc ? units * 4 * R * 4 : 0);
+    L.nrm_b = take(tc ? units * 128 * 4 : 0);
   }
   // generic kernels (also the backward fallback of the tcgen05 forward): per-CTA scratch
   long long pairs = (long long)Bv * Bt;

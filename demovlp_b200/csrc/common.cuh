@@ -86,6 +86,7 @@ struct Workspace {
   size_t dvh, dth;           // fp32 (Bv,R,d), (Bt,W,d)
   size_t dgv, dgt;           // fp32 (Bv,R,R), (Bt,W,W)
   size_t pa, pb;             // tcgen05 backward: bf16 P tiles (Bv * ceil(Bt/4), R, 128) spilled for grad_gemm.cu
+  size_t nrm_a, nrm_b;       // tcgen05: attention l2-norm factors per unit, (units,4,R) and (units,128), forward -> backward
   size_t scratch;            // generic kernels: per-CTA pair scratch
   size_t total;
   int n_cta;                 // generic kernels: persistent grid size

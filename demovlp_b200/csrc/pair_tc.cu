@@ -65,6 +65,7 @@ struct Args {
   float lam2;        // lambda * log2(e)
   int focal;
   float* scores;
+  float *nrm_a, *nrm_b;   // per unit: [4][R] and [128] attention l2-norm factors, kept for the backward
 };
 
 template <int R>
@@ -102,7 +103,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 3) {
     tmem_alloc(sbase + L::TMEMPTR, 512);
     tmem_relinquish();
   }
@@ -117,7 +118,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
 
   if (warp < 4) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-   if (warp == 0) {
+   if (warp == 2) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       for (int k = 0; k < n_tiles; ++k) {
@@ -141,9 +142,14 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         bulk_load(sbase + L::M2T + set * 512, a.m2t + (size_t)jt * kRows, 512, bar(GT_FULL0 + set));
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 3) {
     // ================================ MMA issuer ================================
+    // (warps 2/3: SMSPs 2 and 3 carry the least group work, so the single issuing thread is not starved;
+    //  descriptor words are loop invariant, a K step adds a constant to the low word)
     constexpr uint32_t idS1 = idesc_bf16(128, R), idS2 = idesc_bf16(128, 128), idY2 = idesc_bf16(128, 32);
+    const uint32_t hiK = desc_hi(1024);
+    const uint32_t loT = desc_lo(sbase + L::T), loV = desc_lo(sbase + L::V), loGV = desc_lo(sbase + L::GV);
+    const uint32_t loQ1 = desc_lo(sbase + L::Q1), loQ2 = desc_lo(sbase + L::Q2);
     int vloads = 0;
     auto issue_S = [&](int k) {
       const int set = k & 1;
@@ -153,17 +159,15 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       tc_fence_after();
       if (lane == 0) {
         const uint32_t dS1 = tmem + set * 256, dS2 = tmem + set * 256 + 128;
-#pragma unroll 1
+#pragma unroll
         for (int ks = 0; ks < 16; ++ks) {
-          const uint32_t c = ks >> 2, sub = (ks & 3) * 32;
-          mma_bf16(dS1, smem_desc_sw128(sbase + L::T + c * kTileBytes + sub, 1024),
-                   smem_desc_sw128(sbase + L::V + c * L::kVChunk + sub, 1024), idS1, ks != 0);
+          const uint32_t oT = ((ks >> 2) * kTileBytes + (ks & 3) * 32) >> 4, oV = ((ks >> 2) * L::kVChunk + (ks & 3) * 32) >> 4;
+          mma_bf16_w(dS1, loT + oT, hiK, loV + oV, hiK, idS1, ks != 0);
         }
-#pragma unroll 1
+#pragma unroll
         for (int ks = 0; ks < 16; ++ks) {
-          const uint32_t c = ks >> 2, sub = (ks & 3) * 32;
-          mma_bf16(dS2, smem_desc_sw128(sbase + L::V + c * L::kVChunk + sub, 1024),
-                   smem_desc_sw128(sbase + L::T + c * kTileBytes + sub, 1024), idS2, ks != 0);
+          const uint32_t oT = ((ks >> 2) * kTileBytes + (ks & 3) * 32) >> 4, oV = ((ks >> 2) * L::kVChunk + (ks & 3) * 32) >> 4;
+          mma_bf16_w(dS2, loV + oV, hiK, loT + oT, hiK, idS2, ks != 0);
         }
         tc_commit(bar(S_FULL0 + set));
         tc_commit(bar(T_EMPTY));
@@ -180,10 +184,10 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       mbar_wait(bar(Q1_FULL), k & 1);
       tc_fence_after();
       if (lane == 0) {
-#pragma unroll 1
+#pragma unroll
         for (int s = 0; s < R / 16; ++s)
-          mma_bf16(tmem + set * 256, smem_desc_sw128(sbase + L::Q1 + (s / 4) * kTileBytes + (s % 4) * 32, 1024),
-                   smem_desc_sw128(sbase + L::GV + (s / 4) * L::kVChunk + (s % 4) * 32, 1024), idS1, s != 0);
+          mma_bf16_w(tmem + set * 256, loQ1 + (((s / 4) * kTileBytes + (s % 4) * 32) >> 4), hiK,
+                     loGV + (((s / 4) * L::kVChunk + (s % 4) * 32) >> 4), hiK, idS1, s != 0);
         tc_commit(bar(Y1_FULL0 + set));
       }
       __syncwarp();
@@ -192,13 +196,13 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       mbar_wait(bar(GT_FULL0 + set), (k >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
-#pragma unroll 1
+        const uint32_t loGT = desc_lo(sbase + L::GT + set * kTileBytes);
+#pragma unroll
         for (int t = 0; t < kTPT; ++t)
-#pragma unroll 1
+#pragma unroll
           for (int s = 0; s < 2; ++s)
-            mma_bf16(tmem + set * 256 + 128 + t * 32,
-                     smem_desc_sw128(sbase + L::Q2 + (t / 2) * kTileBytes + (t % 2) * 64 + s * 32, 1024),
-                     smem_desc_sw128(sbase + L::GT + set * kTileBytes + t * 4096 + s * 32, 1024), idY2, s != 0);
+            mma_bf16_w(tmem + set * 256 + 128 + t * 32, loQ2 + (((t / 2) * kTileBytes + (t % 2) * 64 + s * 32) >> 4), hiK,
+                       loGT + ((t * 4096 + s * 32) >> 4), hiK, idY2, s != 0);
         tc_commit(bar(Y2_FULL0 + set));
       }
       __syncwarp();
@@ -237,7 +241,11 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
 #pragma unroll
         for (int h = 0; h < 4; ++h) { float l = leaky(S[r + h]); acc4[h] = fmaf(l, l, acc4[h]); }
       }
-      s_invnB[m] = 1.f / (sqrtf((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + kEps);
+      {
+        const float inb = 1.f / (sqrtf((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + kEps);
+        s_invnB[m] = inb;
+        a.nrm_b[(size_t)(u0 + k) * kRows + m] = inb;
+      }
       named_bar_sync(1, kGroup);             // norms exchanged between the groups
       // pass 2: A = L / n_r ; e = exp(lambda (A + mask_r) - lambda) ; focal ; numerator
       acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.f;
@@ -339,7 +347,11 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             s4[2] = fmaf(l2, l2, s4[2]); s4[3] = fmaf(l3, l3, s4[3]);
           }
           const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-          if (active) s_invnA[t * R + r] = 1.f / (sqrtf(ss) + kEps);
+          if (active) {
+            const float ina = 1.f / (sqrtf(ss) + kEps);
+            s_invnA[t * R + r] = ina;
+            a.nrm_a[((size_t)(u0 + k) * kTPT + t) * R + r] = ina;
+          }
         }
       }
       named_bar_sync(1, kGroup);
@@ -426,7 +438,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 3) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------ host side
@@ -477,6 +489,7 @@ static int launch_fwd(const void* vb, const void* tb, int Bv, int Bt, float lamb
   a.alpha = (const float*)(ws + Lw.alpha); a.beta = (const float*)(ws + Lw.beta);
   a.m2v = (const float*)(ws + Lw.m2v); a.m2t = (const float*)(ws + Lw.m2t);
   a.lam2 = lambda * kLog2e; a.focal = focal; a.scores = scores;
+  a.nrm_a = (float*)(ws + Lw.nrm_a); a.nrm_b = (float*)(ws + Lw.nrm_b);
   int dev = 0, sms = 148;
   DVLP_CUDA_OK(cudaGetDevice(&dev));
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

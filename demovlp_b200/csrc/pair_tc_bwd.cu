@@ -67,8 +67,8 @@ struct Lay {
   static_assert(kAlloc <= 232448, "shared memory budget");
 };
 
-enum Bar { V_FULL = 0, T_FULL, GT_FULL, T_EMPTY, S_DONE, U_READY, Y_DONE, UD_READY, DG_DONE, P_READY, P_STORED,
-           kNumBars };
+enum Bar { V_FULL = 0, T_FULL, GT_FULL, T_EMPTY, S_DONE, U1_READY, U2_READY, Y1_DONE, Y2_DONE, UD1_READY, UD2_READY,
+           DGV_DONE, DGT_DONE, P_READY, P_STORED, kNumBars };
 
 // TMEM columns (everything is per-tile scratch, reused phase by phase)
 constexpr uint32_t cS1 = 0, cS2 = 128, cY2 = 256, cDGT = 384;
@@ -77,6 +77,7 @@ struct Args {
   int Bv, Bt, tiles_per_video;
   long long total_units;
   const float *alpha, *beta, *m2v, *m2t, *d_scores;
+  const float *nrm_a, *nrm_b;   // attention l2-norm factors written by the forward kernel (pair_tc.cu)
   float lam, lam2;
   int focal;
   float *dgv, *dgt;
@@ -161,12 +162,14 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
     prefetch_tmap(&mapPa); prefetch_tmap(&mapPb);
     for (int i = 0; i < kNumBars; ++i) {
       uint32_t cnt = 1;
-      if (i == U_READY || i == UD_READY || i == P_READY) cnt = 384;
+      if (i == U1_READY || i == UD1_READY) cnt = 128;
+      if (i == U2_READY || i == UD2_READY) cnt = 256;
+      if (i == P_READY) cnt = 384;
       mbar_init(bar(i), cnt);
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 3) {
     tmem_alloc(sbase + L::TMEMPTR, 512);
     tmem_relinquish();
   }
@@ -197,32 +200,82 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           bulk_load(sbase + L::ALPHA, a.alpha + (size_t)i * R, R * 4, bar(V_FULL));
           bulk_load(sbase + L::M2V, a.m2v + (size_t)i * R, R * 4, bar(V_FULL));
         }
-        mbar_arrive_expect_tx(bar(GT_FULL), kTileBytes + 1024);
+        mbar_arrive_expect_tx(bar(GT_FULL), kTileBytes + 1024 + 4 * R * 4 + 512);
+        bulk_load(sbase + L::INVNA, a.nrm_a + (size_t)(u0 + k) * kTPT * R, 4 * R * 4, bar(GT_FULL));
+        bulk_load(sbase + L::INVNB, a.nrm_b + (size_t)(u0 + k) * kRows, 512, bar(GT_FULL));
         tma_load_2d(sbase + L::GT, &mapGT, 0, jt * kRows, bar(GT_FULL));
         bulk_load(sbase + L::BETA, a.beta + (size_t)jt * kRows, 512, bar(GT_FULL));
         bulk_load(sbase + L::M2T, a.m2t + (size_t)jt * kRows, 512, bar(GT_FULL));
       }
     } else if (warp == 1) {
-      // ================================ MMA issuer ================================
+      // ============== P stores: the two bf16 P tiles of each unit leave through TMA (grad_gemm.cu) ==============
+      if (lane == 0) {
+        for (int k = 0; k < n_tiles; ++k) {
+          mbar_wait(bar(P_READY), k & 1);
+          const int row = (int)((u0 + k) * R);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tma_store_2d(&mapPa, sbase + L::A1 + c * L::kVChunk, c * 64, row);
+            tma_store_2d(&mapPb, sbase + L::B1 + c * L::kVChunk, c * 64, row);
+          }
+          bulk_commit();
+          bulk_wait_read0();                 // the staging tiles may be overwritten (next tile's U)
+          mbar_arrive(bar(P_STORED));
+        }
+        bulk_wait_all();                     // global writes complete before the CTA retires
+      }
+    } else if (warp == 2) {
+      // ================== MMA issuer, t2i (group B) chain: Y2 = U2 G^T, dG^T = UD2^T U2 ==================
+      constexpr uint32_t idY2 = idesc_bf16(128, 32);
+      constexpr uint32_t idDGT = idesc_bf16(128, 128, 1, 1);       // UD2^T U2: both MN-major
+      constexpr uint32_t CH = L::kVChunk;
+      const uint32_t hiK = desc_hi(1024);
+      const uint32_t loGT = desc_lo(sbase + L::GT), loB1 = desc_lo(sbase + L::B1);
+      const uint32_t loB1m = desc_lo(sbase + L::B1, CH), loB2m = desc_lo(sbase + L::B2, CH);
+      for (int k = 0; k < n_tiles; ++k) {
+        const uint32_t ph = k & 1;
+        if (k > 0) mbar_wait(bar(P_READY), (k - 1) & 1);   // group A has read dG^T of tile k-1
+        mbar_wait(bar(U2_READY), ph);
+        mbar_wait(bar(GT_FULL), ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int t = 0; t < kTPT; ++t)
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+              mma_bf16_w(tmem + cY2 + t * 32, loB1 + (((t >> 1) * CH + (t & 1) * 64 + s * 32) >> 4), hiK,
+                         loGT + ((t * 4096 + s * 32) >> 4), hiK, idY2, s != 0);
+          tc_commit(bar(Y2_DONE));
+        }
+        __syncwarp();
+        mbar_wait(bar(UD2_READY), ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < R / 16; ++ks)
+            mma_bf16_w(tmem + cDGT, loB2m + ((ks * 2048) >> 4), hiK, loB1m + ((ks * 2048) >> 4), hiK, idDGT, ks != 0);
+          tc_commit(bar(DGT_DONE));
+        }
+        __syncwarp();
+      }
+    } else if (warp == 3) {
+      // ========= MMA issuer: S GEMMs and the i2t (group A) chain: Y1 = U1 G^V, dG^V = UD1^T U1 =========
       // Descriptors are loop invariant: their words are built once and every MMA only adds a constant to
       // the 14-bit address field (a single thread issuing dependent 64-bit arithmetic per MMA cost ~130
       // cycles per instruction in the first version of this kernel).
-      constexpr uint32_t idS1 = idesc_bf16(128, R), idS2 = idesc_bf16(128, 128), idY2 = idesc_bf16(128, 32);
+      constexpr uint32_t idS1 = idesc_bf16(128, R), idS2 = idesc_bf16(128, 128);
       constexpr uint32_t idY1 = idesc_bf16(128, R, 1, 0);          // A = U1 (MN-major view of U1^T)
-      constexpr uint32_t idDGT = idesc_bf16(128, 128, 1, 1);       // UD2^T U2: both MN-major
       constexpr uint32_t CH = L::kVChunk;                          // chunk stride of R-row buffers
       const uint32_t hiK = desc_hi(1024);                          // K-major tiles: 8-row groups 1024 B apart
       const uint32_t loT = desc_lo(sbase + L::T), loV = desc_lo(sbase + L::V), loGV = desc_lo(sbase + L::GV);
-      const uint32_t loGT = desc_lo(sbase + L::GT);
       const uint32_t loA1 = desc_lo(sbase + L::A1), loA2 = desc_lo(sbase + L::A2);
-      const uint32_t loB1 = desc_lo(sbase + L::B1), loB2 = desc_lo(sbase + L::B2);
-      const uint32_t loA1m = desc_lo(sbase + L::A1, CH), loB1m = desc_lo(sbase + L::B1, CH);   // MN-major views
-      const uint32_t loB2m = desc_lo(sbase + L::B2, CH);
+      const uint32_t loA1m = desc_lo(sbase + L::A1, CH);           // MN-major view
       int vloads = 0;
       for (int k = 0; k < n_tiles; ++k) {
         const uint32_t ph = k & 1;
         if (is_switch(k)) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
         mbar_wait(bar(T_FULL), ph);
+        if (k > 0) mbar_wait(bar(P_READY), (k - 1) & 1);   // both groups are done with the TMEM of tile k-1
         tc_fence_after();
         TR(1, 0);
         if (lane == 0) {
@@ -241,9 +294,8 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         }
         __syncwarp();
         TR(1, 1);
-        // ---- Y1 = U1 G^V (A: MN-major from U1^T), Y2 = U2 G^T
-        mbar_wait(bar(U_READY), ph);
-        mbar_wait(bar(GT_FULL), ph);
+        // ---- Y1 = U1 G^V (A: MN-major from U1^T)
+        mbar_wait(bar(U1_READY), ph);
         tc_fence_after();
         TR(1, 2);
         if (lane == 0) {
@@ -251,19 +303,12 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           for (int ks = 0; ks < R / 16; ++ks)
             mma_bf16_w(tmem + cS1, loA1m + ((ks * 2048) >> 4), hiK, loGV + (((ks >> 2) * CH + (ks & 3) * 32) >> 4), hiK,
                        idY1, ks != 0);
-#pragma unroll
-          for (int t = 0; t < kTPT; ++t)
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-              mma_bf16_w(tmem + cY2 + t * 32, loB1 + (((t >> 1) * CH + (t & 1) * 64 + s * 32) >> 4), hiK,
-                         loGT + ((t * 4096 + s * 32) >> 4), hiK, idY2, s != 0);
-          tc_commit(bar(Y_DONE));
+          tc_commit(bar(Y1_DONE));
         }
         __syncwarp();
         TR(1, 3);
         // ---- dG^V = UD1^T(K-major rows=regions) x U1^T(K-major rows=regions), K = 128 words
-        //      dG^T = UD2^T U2 : A, B MN-major (M, N = words), K = regions
-        mbar_wait(bar(UD_READY), ph);
+        mbar_wait(bar(UD1_READY), ph);
         tc_fence_after();
         TR(1, 4);
         if (lane == 0) {
@@ -272,31 +317,11 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             const uint32_t o = ((ks >> 2) * CH + (ks & 3) * 32) >> 4;
             mma_bf16_w(tmem + cS1, loA2 + o, hiK, loA1 + o, hiK, idS1, ks != 0);
           }
-#pragma unroll
-          for (int ks = 0; ks < R / 16; ++ks)
-            mma_bf16_w(tmem + cDGT, loB2m + ((ks * 2048) >> 4), hiK, loB1m + ((ks * 2048) >> 4), hiK, idDGT, ks != 0);
-          tc_commit(bar(DG_DONE));
+          tc_commit(bar(DGV_DONE));
         }
         __syncwarp();
         TR(1, 5);
-        // ---- the two P tiles of this unit leave through TMA stores (grad_gemm.cu contracts them)
-        mbar_wait(bar(P_READY), ph);
-        TR(1, 6);
-        if (lane == 0) {
-          const int row = (int)((u0 + k) * R);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            tma_store_2d(&mapPa, sbase + L::A1 + c * CH, c * 64, row);
-            tma_store_2d(&mapPb, sbase + L::B1 + c * CH, c * 64, row);
-          }
-          bulk_commit();
-          bulk_wait_read0();                 // the staging tiles may be overwritten (next tile's U)
-          mbar_arrive(bar(P_STORED));
-        }
-        __syncwarp();
-        TR(1, 7);
       }
-      if (lane == 0) bulk_wait_all();        // global writes complete before the CTA retires
     }
   } else if (warp < 8) {
     // ================== group A: i2t direction, thread = word row ==================
@@ -329,19 +354,16 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         for (int c = 0; c < R / 16; ++c) tmem_ld16(tmem + cS1 + lane_off + c * 16, raw + c * 16);
         tmem_ld_wait();
       }
-      float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+      // the query-axis l2 norms of model/loss.py:238 come from the forward kernel (nrm_a / nrm_b, loaded with
+      // the per-tile vectors): no norm pass and no exchange between the two groups in the backward
 #pragma unroll
       for (int r = 0; r < R; r += 4) {
         const float4 al = *reinterpret_cast<const float4*>(s_alpha + r);
         S[r + 0] *= beta_m * al.x; S[r + 1] *= beta_m * al.y; S[r + 2] *= beta_m * al.z; S[r + 3] *= beta_m * al.w;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) { float l = leaky(S[r + h]); acc4[h] = fmaf(l, l, acc4[h]); }
       }
-      s_invnB[m] = 1.f / (sqrtf((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + kEps);
-      TRA(2);
-      named_bar_sync(1, kGroup);
       TRA(3);
       if (k > 0) mbar_wait(bar(P_STORED), (k - 1) & 1);   // TMA stores of tile k-1 have read A1 / B1
+      float acc4[4];
       // forward pass 2 (e kept in Y[] until the focal threshold is known)
       acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.f;
 #pragma unroll
@@ -368,10 +390,10 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       }
       const float num = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
       fence_proxy_async();
-      mbar_arrive(bar(U_READY));
+      mbar_arrive(bar(U1_READY));
       TRA(4);
       // ---- denominators and per-word scalars
-      mbar_wait(bar(Y_DONE), ph);
+      mbar_wait(bar(Y1_DONE), ph);
       tc_fence_after();
       TRA(5);
       {
@@ -406,7 +428,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       }
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(bar(UD_READY));
+      mbar_arrive(bar(UD1_READY));
       TRA(6);
       // ---- t_r = sum over this text's words of A dA  (l2-norm backward, model/loss.py:238)
       {
@@ -436,7 +458,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         __syncwarp();
       }
       TRA(7);
-      mbar_wait(bar(DG_DONE), ph);                     // U1^T / UD1^T consumed: A1 may take P1^T
+      mbar_wait(bar(DGV_DONE), ph);                    // U1^T / UD1^T consumed: A1 may take P1^T
       TRA(8);
       // pass B3: dS = (dA - A t) / n * leaky'(S) + c1 u ;  P = dS alpha_r beta_w
 #pragma unroll
@@ -456,6 +478,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         }
       }
       // dG^T block of this text: rows = this word, 32 columns
+      mbar_wait(bar(DGT_DONE), ph);
       tc_fence_after();
       {
         float gt[32];
@@ -466,6 +489,21 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           float* dst = a.dgt + ((size_t)jt * kRows + m) * kW;
 #pragma unroll
           for (int c = 0; c < 32; c += 4) red_add_v4(dst + c, gt[c], gt[c + 1], gt[c + 2], gt[c + 3]);
+        }
+      }
+      // dG^V rows (TMEM lanes = regions: this warp's quadrant holds regions 32q..32q+31); group B is the
+      // critical path of the tile, group A has slack
+      if (q * 32 < R) {
+        float* dst = a.dgv + ((size_t)i * R + m) * R;
+#pragma unroll 1
+        for (int c = 0; c < R; c += 16) {
+          float v[16];
+          tmem_ld16(tmem + cS1 + lane_off + c, reinterpret_cast<uint32_t*>(v));
+          tmem_ld_wait();
+          if (m < R) {
+#pragma unroll
+            for (int x4 = 0; x4 < 16; x4 += 4) red_add_v4(dst + c + x4, v[x4], v[x4 + 1], v[x4 + 2], v[x4 + 3]);
+          }
         }
       }
       tc_fence_before();
@@ -500,28 +538,6 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       TRB(1);
       const float alpha_r = active ? s_alpha[r] : 0.f;
       float num[2], c1v[2], kapv[2];
-      if (warp_active) {
-#pragma unroll
-        for (int tt = 0; tt < 2; ++tt) {
-          const int t = t_lo + tt;
-          float x[32];
-          tmem_ld16(tmem + cS2 + lane_off + t * 32, reinterpret_cast<uint32_t*>(x));
-          tmem_ld16(tmem + cS2 + lane_off + t * 32 + 16, reinterpret_cast<uint32_t*>(x) + 16);
-          tmem_ld_wait();
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int w = 0; w < 32; w += 4) {
-            const float4 be = *reinterpret_cast<const float4*>(s_beta + t * 32 + w);
-            float l0 = leaky(x[w] * (alpha_r * be.x)), l1 = leaky(x[w + 1] * (alpha_r * be.y));
-            float l2 = leaky(x[w + 2] * (alpha_r * be.z)), l3 = leaky(x[w + 3] * (alpha_r * be.w));
-            s4[0] = fmaf(l0, l0, s4[0]); s4[1] = fmaf(l1, l1, s4[1]);
-            s4[2] = fmaf(l2, l2, s4[2]); s4[3] = fmaf(l3, l3, s4[3]);
-          }
-          if (active) s_invnA[t * R + r] = 1.f / (sqrtf((s4[0] + s4[1]) + (s4[2] + s4[3])) + kEps);
-        }
-      }
-      TRB(2);
-      named_bar_sync(1, kGroup);
       TRB(3);
       if (k > 0) mbar_wait(bar(P_STORED), (k - 1) & 1);   // TMA stores of tile k-1 have read A1 / B1
       if (warp_active) {
@@ -564,10 +580,10 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         }
       }
       fence_proxy_async();
-      mbar_arrive(bar(U_READY));
+      mbar_arrive(bar(U2_READY));
       TRB(4);
       // ---- loop A: denominators, per-(region, text) scalars, UD2 = u dD
-      mbar_wait(bar(Y_DONE), ph);
+      mbar_wait(bar(Y2_DONE), ph);
       tc_fence_after();
       TRB(5);
       if (warp_active) {
@@ -610,7 +626,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         }
       }
       fence_proxy_async();
-      mbar_arrive(bar(UD_READY));
+      mbar_arrive(bar(UD2_READY));
       TRB(6);
       // ---- loop B: per text, dA, the cross-region sum t_w = sum_r A dA, dS, P2
 #pragma unroll 1
@@ -644,7 +660,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           s_tBp[(t * 4 + q) * 32 + lane] = 0.f;
         }
         named_bar_sync(3 + hb, 128);                   // the four region-quadrant warps of this half
-        if (tt == 0) mbar_wait(bar(DG_DONE), ph);      // U2 / UD2 consumed: B1 may take P2
+        if (tt == 0) mbar_wait(bar(DGT_DONE), ph);     // U2 / UD2 consumed: B1 may take P2
         if (warp_active) {
           const float* tb = s_tBp + t * 128;
 #pragma unroll
@@ -669,22 +685,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
           }
         }
       }
-      // dG^V rows of this region
       TRB(7);
-      tc_fence_after();
-      if (warp_active) {
-        float* dst = a.dgv + ((size_t)i * R + r) * R;
-#pragma unroll 1
-        for (int c = hb * 16; c < R; c += 32) {         // the two halves take alternate 16-column chunks
-          float v[16];
-          tmem_ld16(tmem + cS1 + lane_off + c, reinterpret_cast<uint32_t*>(v));
-          tmem_ld_wait();
-          if (active) {
-#pragma unroll
-            for (int x4 = 0; x4 < 16; x4 += 4) red_add_v4(dst + c + x4, v[x4], v[x4 + 1], v[x4 + 2], v[x4 + 3]);
-          }
-        }
-      }
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar(P_READY));
@@ -694,7 +695,7 @@ k_pair_tc_bwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 3) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------ host side
@@ -747,6 +748,7 @@ static int launch_bwd(const void* vb, const void* tb, int Bv, int Bt, float lamb
   a.d_scores = d_scores;
   a.lam = lambda; a.lam2 = lambda * kLog2e; a.focal = focal;
   a.dgv = (float*)(ws + Lw.dgv); a.dgt = (float*)(ws + Lw.dgt);
+  a.nrm_a = (const float*)(ws + Lw.nrm_a); a.nrm_b = (const float*)(ws + Lw.nrm_b);
   a.trace = (long long*)g_trace_buffer;
   int dev = 0, sms = 148;
   DVLP_CUDA_OK(cudaGetDevice(&dev));
