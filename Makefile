@@ -8,7 +8,7 @@ LIB := demovlp_b200/lib/libdemovlp_b200.so
 
 all: $(LIB)
 
-build/%.o: demovlp_b200/csrc/%.cu demovlp_b200/csrc/common.cuh include/demovlp_b200.h
+build/%.o: demovlp_b200/csrc/%.cu $(wildcard demovlp_b200/csrc/*.cuh) include/demovlp_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 

@@ -14,6 +14,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ------------------------------------------------------------------ mbarrier
+#ifndef DVLP_MBAR_SUSPEND_NS
+#define DVLP_MBAR_SUSPEND_NS 20000
+#endif
+constexpr uint32_t kMbarSuspendNs = DVLP_MBAR_SUSPEND_NS;
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -28,12 +32,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the hardware park the warp (no issue slots spent spinning); it still wakes
+  // as soon as the phase completes
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
   return ok != 0;
 }
@@ -42,7 +48,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 20)) __trap();
   }
 }
 
