@@ -56,6 +56,11 @@ int run_pair_tc_bwd(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int
 bool tc_bwd_available();
 int run_grad_gemm(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
                   const Workspace& L, cudaStream_t st);
+int run_pair_bwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
+                  const float* d_scores, char* ws, const Workspace& L, cudaStream_t st);
+int run_grad_gemm2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
+                   const Workspace& L, cudaStream_t st);
+int tc_bwd_version();
 extern void* g_trace_buffer;
 
 Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc) {
@@ -90,6 +95,9 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
     L.pb = take(tc ? units * R * 128 * 2 : 0);
     L.nrm_a = take(tc ? units * 4 * R * 4 : 0);
     L.nrm_b = take(tc ? units * 128 * 4 : 0);
+    L.rowv = take(tc ? units * 128 * 16 : 0);
+    L.colv = take(tc ? units * 4 * R * 16 : 0);
+    L.gbd = take(tc ? (size_t)((Bt + 3) / 4) * 128 * 128 * 2 : 0);
   }
   // generic kernels (also the backward fallback of the tcgen05 forward): per-CTA scratch
   long long pairs = (long long)Bv * Bt;
@@ -246,8 +254,13 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   if (tc && tc_bwd_available()) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
-    if ((rc = run_pair_tc_bwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, d_scores, ws, L, st))) return rc;
-    if ((rc = run_grad_gemm(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
+    if (tc_bwd_version() == 2) {
+      if ((rc = run_pair_bwd2(vb, tb, Bv, Bt, R, W, d, lambda, d_scores, ws, L, st))) return rc;
+      if ((rc = run_grad_gemm2(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
+    } else {
+      if ((rc = run_pair_tc_bwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, d_scores, ws, L, st))) return rc;
+      if ((rc = run_grad_gemm(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
+    }
     prescaled = 1;
   } else {
     PairArgs a{};

@@ -87,6 +87,9 @@ struct Workspace {
   size_t dgv, dgt;           // fp32 (Bv,R,R), (Bt,W,W)
   size_t pa, pb;             // tcgen05 backward: bf16 P tiles (Bv * ceil(Bt/4), R, 128) spilled for grad_gemm.cu
   size_t nrm_a, nrm_b;       // tcgen05: attention l2-norm factors per unit, (units,4,R) and (units,128), forward -> backward
+  size_t rowv, colv;         // tcgen05: per-unit query scalars saved by the forward for pair_bwd2.cu: float4 (units,128) =
+                             // (nB, thr1, 1/|c1|, cos1) per word, float4 (units,4,R) = (nA, thr2, 1/|c2|, cos2) per (text, region)
+  size_t gbd;                // tcgen05: block-diagonal bf16 text Gram tiles (ceil(Bt/4), 128, 128)
   size_t scratch;            // generic kernels: per-CTA pair scratch
   size_t total;
   int n_cta;                 // generic kernels: persistent grid size

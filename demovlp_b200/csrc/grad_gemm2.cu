@@ -1,0 +1,264 @@
+// Gradient contractions of the region-word backward as dense, accumulator-stationary tcgen05 GEMMs
+// (single-tile variant, partner of pair_bwd2.cu).
+//
+// pair_bwd2.cu leaves, per (video i, 4-text tile jt) unit, ONE bf16 tile
+//     P = (dS_i2t + dS_t2i) * alpha_r * beta_w      [128 words][R regions], 32-byte-swizzle chunks of 16 columns
+// (autograd of model/loss.py:235: S = Vh Th^T  =>  dVh = dS Th, dTh = dS^T Vh).  This file contracts it:
+//
+//   MODE_V   dV'[i]  (R x d)   = sum_jt P[i, jt]^T T_jt      one CTA per video, K loop over text tiles
+//   MODE_T   dT'[jt] (128 x d) = sum_i  P[i, jt]   V_i       one CTA per (text tile, video split)
+//
+// T / V are the RAW bf16 embeddings (the alpha/beta factors are already in P).  The accumulator
+// (128 lanes x 256 fp32 columns) stays in TMEM for the whole K loop, operands arrive by TMA into a
+// 2-stage ring, one elected thread issues the MMAs; MODE_V writes its rows with plain stores (the CTA
+// owns them), MODE_T adds its split's partial sums with red.global (a few MB in total).
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dvlp {
+using namespace ptx;
+
+namespace gg2 {
+constexpr int kD = 256, kRows = 128, kThreads = 192;
+constexpr int kTileBytes = 16384, kCh32 = 4096;
+enum { MODE_V = 0, MODE_T = 1 };
+
+template <int R, int MODE>
+struct Lay {
+  static constexpr int NC = R / 16;                                   // 16-column chunks of the P tile
+  static constexpr int CH = R * 128;                                  // one 64-column chunk of an R-row tile
+  static constexpr int kStages = MODE == MODE_V ? 2 : 3;
+  static constexpr int P = 0, X = NC * kCh32;
+  static constexpr int XBYTES = MODE == MODE_V ? 4 * kTileBytes : 4 * CH;
+  static constexpr int STAGE = NC * kCh32 + XBYTES;
+  static constexpr int BARS = kStages * STAGE;
+  static constexpr int TMEMPTR = BARS + 8 * 8;
+  static constexpr int kAlloc = TMEMPTR + 16;
+  static_assert(kAlloc <= 232448, "shared memory budget");
+};
+
+struct Args {
+  int Bv, Bt, tiles_per_video, videos_per_split;
+  long long text_rows;     // Bt * W: valid rows of dT'
+  float* out;              // MODE_V: dV' (Bv, R, d), overwritten;  MODE_T: dT' (Bt*W, d), accumulated
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapX, Args a) {
+  using L = Lay<R, MODE>;
+  constexpr int kStages = L::kStages, NC = L::NC;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (sbase & 1023u) __trap();
+  volatile uint32_t* s_tmem = (volatile uint32_t*)(smem_raw + L::TMEMPTR);
+  auto full = [&](int s) { return sbase + L::BARS + 8 * s; };
+  auto empty = [&](int s) { return sbase + L::BARS + 8 * (kStages + s); };
+  const uint32_t done = sbase + L::BARS + 8 * (2 * kStages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // this CTA's K loop
+  int i0, n_steps, jt = 0;
+  if (MODE == MODE_V) {
+    i0 = blockIdx.x;                       // video
+    n_steps = a.tiles_per_video;
+  } else {
+    jt = blockIdx.x % a.tiles_per_video;
+    const int z = blockIdx.x / a.tiles_per_video;
+    i0 = z * a.videos_per_split;
+    n_steps = min(a.videos_per_split, a.Bv - i0);
+  }
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapP); prefetch_tmap(&mapX);
+    for (int s = 0; s < 2 * kStages + 1; ++s) mbar_init(sbase + L::BARS + 8 * s, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(sbase + L::TMEMPTR, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int k = 0; k < n_steps; ++k) {
+        const int s = k % kStages, it = k / kStages;
+        if (it > 0) mbar_wait(empty(s), (it - 1) & 1);
+        const uint32_t st = sbase + s * L::STAGE;
+        const long long unit = MODE == MODE_V ? (long long)i0 * a.tiles_per_video + k
+                                              : (long long)(i0 + k) * a.tiles_per_video + jt;
+        mbar_arrive_expect_tx(full(s), L::STAGE);
+        for (int c = 0; c < NC; ++c) tma_load_2d(st + L::P + c * kCh32, &mapP, c * 16, (int)(unit * kRows), full(s));
+        if (MODE == MODE_V) {
+          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * kTileBytes, &mapX, c * 64, k * kRows, full(s));
+        } else {
+          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * L::CH, &mapX, c * 64, (i0 + k) * R, full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idV = idesc_bf16(128, 256, 1, 1);     // P^T (MN-major view, M = regions) x T (MN-major)
+    constexpr uint32_t idT = idesc_bf16(128, 256, 0, 1);     // P (K-major, M = words) x V (MN-major)
+    const uint32_t hiK = desc_hi(1024);
+    const uint32_t hi32 = ((256u >> 4) & 0x3FFF) | (1u << 14) | (6u << 29);   // 32-byte swizzle, 8-row groups 256 B apart
+    for (int k = 0; k < n_steps; ++k) {
+      const int s = k % kStages, it = k / kStages;
+      mbar_wait(full(s), it & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = sbase + s * L::STAGE;
+        if (MODE == MODE_V) {
+          // K = 128 words: P rows are the K rows of an MN-major operand whose M (regions) chunks are 4 KB apart;
+          // M = 128 reads past the R valid regions (into the X tile): those accumulator lanes are never stored
+          const uint32_t loX = desc_lo(st + L::X, kTileBytes);
+          const uint32_t loP = desc_lo(st + L::P, kCh32);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_bf16_w(tmem, loP + ((ks * 512) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idV, (k | ks) != 0);
+        } else {
+          // K = R regions: one 16-column chunk of P per K step
+          const uint32_t loX = desc_lo(st + L::X, L::CH);
+          const uint32_t loP = desc_lo(st + L::P);
+#pragma unroll
+          for (int ks = 0; ks < NC; ++ks)
+            mma_bf16_w(tmem, loP + ((ks * kCh32) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idT, (k | ks) != 0);
+        }
+        tc_commit(empty(s));
+        if (k == n_steps - 1) tc_commit(done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue: thread = accumulator row (TMEM lane quadrant = warp % 4)
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    if (n_steps > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      bool valid;
+      float* dst;
+      if (MODE == MODE_V) {
+        valid = row < R;
+        dst = a.out + ((size_t)i0 * R + row) * kD;
+      } else {
+        const long long grow = (long long)jt * kRows + row;
+        valid = grow < a.text_rows;
+        dst = a.out + (size_t)grow * kD;
+      }
+      const bool warp_valid = MODE == MODE_V ? (q * 32 < R) : true;
+      if (warp_valid) {
+#pragma unroll 1
+        for (int c = 0; c < kD; c += 32) {
+          float v[32];
+          tmem_ld16(tmem + lane_off + c, reinterpret_cast<uint32_t*>(v));
+          tmem_ld16(tmem + lane_off + c + 16, reinterpret_cast<uint32_t*>(v) + 16);
+          tmem_ld_wait();
+          if (valid) {
+            if (MODE == MODE_V) {
+#pragma unroll
+              for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + c + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+            } else {
+#pragma unroll
+              for (int x = 0; x < 32; x += 4) red_add_v4(dst + c + x, v[x], v[x + 1], v[x + 2], v[x + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                    uint32_t box_cols = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return DVLP_ERR_CUDA;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return DVLP_ERR_CUDA; }
+  return DVLP_OK;
+}
+
+template <int R>
+static int launch(const void* vb, const void* tb, int Bv, int Bt, int W, char* ws, const Workspace& Lw, cudaStream_t st) {
+  const int tiles = (Bt + 3) / 4;
+  const long long units = (long long)Bv * tiles;
+  CUtensorMap mP, mT, mV;
+  int rc;
+  if ((rc = make_map(&mP, ws + Lw.pa, (uint64_t)units * kRows, R, kRows, 16, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&mT, tb, (uint64_t)Bt * W, kD, kRows))) return rc;
+  if ((rc = make_map(&mV, vb, (uint64_t)Bv * R, kD, R))) return rc;
+  int dev = 0, sms = 148;
+  DVLP_CUDA_OK(cudaGetDevice(&dev));
+  DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_grad_gemm2<R, MODE_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<R, MODE_V>::kAlloc));
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_grad_gemm2<R, MODE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<R, MODE_T>::kAlloc));
+    attr_set = true;
+  }
+  Args a{};
+  a.Bv = Bv; a.Bt = Bt; a.tiles_per_video = tiles; a.text_rows = (long long)Bt * W;
+  // dV': one CTA per video
+  a.videos_per_split = Bv;
+  a.out = (float*)(ws + Lw.dvh);
+  k_grad_gemm2<R, MODE_V><<<Bv, kThreads, Lay<R, MODE_V>::kAlloc, st>>>(mP, mT, a);
+  DVLP_LAUNCH_OK();
+  // dT': text tiles x video splits ~ one wave of CTAs
+  int splits = sms / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > Bv) splits = Bv;
+  a.videos_per_split = (Bv + splits - 1) / splits;
+  splits = (Bv + a.videos_per_split - 1) / a.videos_per_split;
+  a.out = (float*)(ws + Lw.dth);
+  k_grad_gemm2<R, MODE_T><<<tiles * splits, kThreads, Lay<R, MODE_T>::kAlloc, st>>>(mP, mV, a);
+  DVLP_LAUNCH_OK();
+  return DVLP_OK;
+}
+}  // namespace gg2
+
+// dV' (overwritten) and dT' (accumulated: the caller zeroes it) from the P tiles pair_bwd2.cu stored
+int run_grad_gemm2(const void* vb, const void* tb, int Bv, int Bt, int R, int W, int d, char* ws, const Workspace& L,
+                  cudaStream_t st) {
+  if (d != gg2::kD || W != 32) return DVLP_ERR_BAD_SHAPE;
+  switch (R) {
+    case 80: return gg2::launch<80>(vb, tb, Bv, Bt, W, ws, L, st);
+    case 64: return gg2::launch<64>(vb, tb, Bv, Bt, W, ws, L, st);
+    case 48: return gg2::launch<48>(vb, tb, Bv, Bt, W, ws, L, st);
+    case 32: return gg2::launch<32>(vb, tb, Bv, Bt, W, ws, L, st);
+  }
+  return DVLP_ERR_BAD_SHAPE;
+}
+
+}  // namespace dvlp

@@ -1,0 +1,574 @@
+// Region-word pair scores on tcgen05 / TMEM / TMA (sm_100a): BACKWARD kernel, single-orientation design.
+//
+// Back-propagates d_scores through both attention directions of model/loss.py:209-330 for one
+// (video, 4-text tile) unit at a time, recomputing the attention from the raw similarities (nothing of size
+// Bv*Bt*R*W is ever stored).  Everything lives in ONE orientation: TMEM lane = word row (4 texts x 32 words),
+// TMEM column = region.  The R columns are split into 16-column chunks, one compute warpgroup per chunk
+// (R/16 warpgroups, all running the same code), so every element (word, region) is owned by exactly one
+// thread which evaluates BOTH directions for it and emits ONE gradient tile
+//     P = (dS_i2t + dS_t2i) * alpha_r * beta_w                      [128 words][R regions] bf16
+// that grad_gemm.cu contracts against T / V.  Sums over regions (softmax axis of the i2t direction, l2-norm
+// axis of t2i) are row sums: per-thread partials exchanged between the warpgroups through shared memory.
+// Sums over the words of a text (softmax axis of t2i, l2-norm axis of i2t) are sums over the 32 lanes of
+// one warp: shuffle transpose-reductions.  The per-query scalars of the forward (attention l2 norms, focal
+// thresholds, 1/|c|, cosine) are not recomputed: pair_tc.cu saves them per unit (rowv / colv).
+//
+// Tensor-core products per unit (all operands in shared memory, accumulators in TMEM):
+//   S   = T V^T                     M=128 words, N=R, K=256      raw similarities
+//   Y1  = U1 G^V                    M=128, N=R, K=R              i2t: Gram-form |weighted context|^2
+//   Y2  = Gbd U2                    M=128, N=R, K=128            t2i: Gbd = block-diagonal text Gram matrices
+//   dGV += UD1^T U1                 M=R(128), N=R, K=128         accumulated in TMEM over the tiles of a video
+//   dGT = UD2 U2^T                  M=128, N=128, K=R            diagonal 32x32 blocks used
+// U / UD / P tiles are [word rows][region columns] in the 32-byte-swizzle layout (one 4 KB chunk per 16
+// columns): written row-wise by their owner threads, consumed K-major or MN-major through the UMMA
+// descriptors (encodings checked by tools/ubench/desc_lab.cu).
+//
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 P-tile TMA stores, warp 3 TMEM owner,
+// warps 4.. compute (warpgroup g = column chunk, warp q of the group = text slot = TMEM lane quadrant).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dvlp {
+using namespace ptx;
+
+namespace tb2 {
+constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128;
+constexpr int kTileBytes = 16384;   // 128 rows x 128 B (one 64-column chunk of a 128-byte-swizzle tile)
+constexpr int kCh32 = 4096;         // 128 rows x 32 B  (one 16-column chunk of a 32-byte-swizzle tile)
+
+template <int R>
+struct Lay {
+  static constexpr int NC = R / 16;                 // column chunks = compute warpgroups
+  static constexpr int NW = 4 * NC;                 // compute warps
+  static constexpr int kThreads = 128 * (1 + NC);
+  static constexpr int kVChunk = R * 128;
+  static constexpr int V = 0;                       // 4 chunks (K = 256)
+  static constexpr int GV = V + 4 * kVChunk;        // 2 chunks
+  static constexpr int T = GV + 2 * kVChunk;        // 4 x 16 KB; dead after the S GEMM: UD1 / UD2 alias it
+  static constexpr int UD1 = T, UD2 = T + 2 * kTileBytes;
+  static constexpr int GBD = T + 4 * kTileBytes;    // 2 x 16 KB
+  static constexpr int U1 = GBD + 2 * kTileBytes;   // NC x 4 KB; re-used for P
+  static constexpr int U2 = U1 + NC * kCh32;
+  static constexpr int ROWV = U2 + NC * kCh32;      // [128] float4 (nB, thr1, rden1, cos1)
+  static constexpr int COLV = ROWV + 2048;          // [4][R] float4 (nA, thr2, rden2, cos2)
+  static constexpr int BETA = COLV + 4 * R * 16;    // [128]
+  static constexpr int M2T = BETA + 512;            // [128]
+  static constexpr int ALPHA = M2T + 512;           // [R]
+  static constexpr int M2V = ALPHA + R * 4;         // [R]
+  static constexpr int TAB = M2V + R * 4;           // per compute warp 3 x [16] float4
+  static constexpr int TBP = TAB + NW * 768;        // [NC][128] partial row sums
+  static constexpr int BARS = TBP + NC * 512;
+  static constexpr int TMEMPTR = BARS + 16 * 8;
+  static constexpr int kAlloc = TMEMPTR + 16;
+  static_assert(NC * kCh32 <= 2 * kTileBytes, "UD tiles must fit the T alias");
+  static_assert(kAlloc <= 232448, "shared memory budget");
+};
+
+enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE, U_READY, Y_DONE, UD_READY, DG_DONE, P_READY,
+           P_STORED, kNumBars };
+
+// TMEM columns
+constexpr uint32_t cS = 0, cY1 = 96, cY2 = 192, cDGV = 288, cDGT = 384;
+
+struct Args {
+  int Bv, Bt, tiles_per_video;
+  long long total_units;
+  const float *alpha, *beta, *m2v, *m2t, *d_scores;
+  const float4 *rowv, *colv;     // per-unit scalars saved by the forward kernel
+  float lam, lam2;
+  float *dgv, *dgt;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t desc_hi32(uint32_t sbo_bytes) {      // 32-byte swizzle
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (6u << 29);
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+// 16 columns: lane l ends with the 32-lane sum of v[l & 15].
+__device__ __forceinline__ float lanes_to_columns16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      float send = up ? v[i] : v[i + h];
+      float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+template <int R>
+__global__ void __launch_bounds__(Lay<R>::kThreads, 1)
+k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapT,
+            const __grid_constant__ CUtensorMap mapGV, const __grid_constant__ CUtensorMap mapGBD,
+            const __grid_constant__ CUtensorMap mapP, Args a) {
+  using L = Lay<R>;
+  constexpr int NC = L::NC, NW = L::NW;
+  static_assert(R % 16 == 0 && R >= 32 && R <= 80, "R must be a multiple of 16 in [32,80]");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (sbase & 1023u) __trap();
+  uint8_t* sgen = smem_raw;
+  volatile uint32_t* s_tmem = (volatile uint32_t*)(sgen + L::TMEMPTR);
+  auto bar = [&](int i) { return sbase + L::BARS + 8 * i; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u0 = a.total_units * blockIdx.x / gridDim.x;
+  const long long u1 = a.total_units * (blockIdx.x + 1) / gridDim.x;
+  const int n_tiles = (int)(u1 - u0);
+  const int i0 = (int)(u0 / a.tiles_per_video), jt0 = (int)(u0 % a.tiles_per_video);
+  const int tpv = a.tiles_per_video;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapV); prefetch_tmap(&mapT); prefetch_tmap(&mapGV); prefetch_tmap(&mapGBD); prefetch_tmap(&mapP);
+    for (int b = 0; b < kNumBars; ++b) {
+      uint32_t cnt = 1;
+      if (b == VEC_FREE || b == U_READY || b == UD_READY || b == P_READY) cnt = NW;
+      mbar_init(bar(b), cnt);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 3) {
+    tmem_alloc(sbase + L::TMEMPTR, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 4) {
+    if (NC == 5) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 0) {
+      // =============================== TMA producer ===============================
+      if (lane == 0) {
+        int i = i0, jt = jt0;
+        for (int k = 0; k < n_tiles; ++k) {
+          const uint32_t pp = (k - 1) & 1;
+          const long long unit = u0 + k;
+          // per-unit / per-tile vectors: the staging area is free once every warp has built its tables
+          if (k > 0) mbar_wait(bar(VEC_FREE), pp);
+          mbar_arrive_expect_tx(bar(VEC_FULL), 2048 + 4 * R * 16 + 1024);
+          bulk_load(sbase + L::ROWV, a.rowv + unit * kRows, 2048, bar(VEC_FULL));
+          bulk_load(sbase + L::COLV, a.colv + unit * (kTPT * R), 4 * R * 16, bar(VEC_FULL));
+          bulk_load(sbase + L::BETA, a.beta + (size_t)jt * kRows, 512, bar(VEC_FULL));
+          bulk_load(sbase + L::M2T, a.m2t + (size_t)jt * kRows, 512, bar(VEC_FULL));
+          // block-diagonal text Gram tile: the Y2 GEMM of the previous tile has read it
+          if (k > 0) mbar_wait(bar(Y_DONE), pp);
+          mbar_arrive_expect_tx(bar(GBD_FULL), 2 * kTileBytes);
+          for (int c = 0; c < 2; ++c) tma_load_2d(sbase + L::GBD + c * kTileBytes, &mapGBD, c * 64, jt * kRows, bar(GBD_FULL));
+          // text tile: its buffer doubles as UD1 / UD2 until the dG GEMMs of the previous tile are done
+          if (k > 0) mbar_wait(bar(DG_DONE), pp);
+          mbar_arrive_expect_tx(bar(T_FULL), 4 * kTileBytes);
+          for (int c = 0; c < 4; ++c) tma_load_2d(sbase + L::T + c * kTileBytes, &mapT, c * 64, jt * kRows, bar(T_FULL));
+          if (k == 0 || jt == 0) {
+            // the resident video changes: everybody is done with tile k-1
+            if (k > 0) mbar_wait(bar(P_READY), pp);
+            mbar_arrive_expect_tx(bar(V_FULL), 6 * L::kVChunk + 2 * R * 4);
+            for (int c = 0; c < 4; ++c) tma_load_2d(sbase + L::V + c * L::kVChunk, &mapV, c * 64, i * R, bar(V_FULL));
+            for (int c = 0; c < 2; ++c) tma_load_2d(sbase + L::GV + c * L::kVChunk, &mapGV, c * 64, i * R, bar(V_FULL));
+            bulk_load(sbase + L::ALPHA, a.alpha + (size_t)i * R, R * 4, bar(V_FULL));
+            bulk_load(sbase + L::M2V, a.m2v + (size_t)i * R, R * 4, bar(V_FULL));
+          }
+          if (++jt == tpv) { jt = 0; ++i; }
+        }
+      }
+    } else if (warp == 1) {
+      // ================================ MMA issuer ================================
+      constexpr uint32_t idS = idesc_bf16(128, R), idY2 = idesc_bf16(128, R, 0, 1), idDGV = idesc_bf16(128, R, 1, 1);
+      constexpr uint32_t idDGT = idesc_bf16(128, 128);
+      constexpr uint32_t CH = L::kVChunk;
+      const uint32_t hi128 = desc_hi(1024), hi32 = desc_hi32(256);
+      const uint32_t loT = desc_lo(sbase + L::T), loV = desc_lo(sbase + L::V), loGV = desc_lo(sbase + L::GV);
+      const uint32_t loGBD = desc_lo(sbase + L::GBD);
+      const uint32_t loU1k = desc_lo(sbase + L::U1), loU2k = desc_lo(sbase + L::U2), loUD2k = desc_lo(sbase + L::UD2);
+      const uint32_t loU1m = desc_lo(sbase + L::U1, kCh32), loU2m = desc_lo(sbase + L::U2, kCh32);
+      const uint32_t loUD1m = desc_lo(sbase + L::UD1, kCh32);
+      int vloads = 0, jt = jt0;
+      auto issue_S = [&](int k, bool sw) {
+        if (sw) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
+        mbar_wait(bar(T_FULL), k & 1);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint32_t oT = ((ks >> 2) * kTileBytes + (ks & 3) * 32) >> 4, oV = ((ks >> 2) * CH + (ks & 3) * 32) >> 4;
+            mma_bf16_w(tmem + cS, loT + oT, hi128, loV + oV, hi128, idS, ks != 0);
+          }
+          tc_commit(bar(S_DONE));
+        }
+        __syncwarp();
+      };
+      issue_S(0, true);
+      for (int k = 0; k < n_tiles; ++k) {
+        const uint32_t ph = k & 1;
+        const bool first_of_video = (k == 0 || jt == 0);
+        // ---- Y1 = U1 G^V,  Y2 = Gbd U2
+        mbar_wait(bar(GBD_FULL), ph);
+        mbar_wait(bar(U_READY), ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < NC; ++ks)
+            mma_bf16_w(tmem + cY1, loU1k + ((ks * kCh32) >> 4), hi32, loGV + (((ks >> 2) * CH + (ks & 3) * 32) >> 4), hi128,
+                       idS, ks != 0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_bf16_w(tmem + cY2, loGBD + (((ks >> 2) * kTileBytes + (ks & 3) * 32) >> 4), hi128, loU2m + ((ks * 512) >> 4),
+                       hi32, idY2, ks != 0);
+          tc_commit(bar(Y_DONE));
+        }
+        __syncwarp();
+        // ---- dGV += UD1^T U1 (K = 128 words),  dGT = UD2 U2^T (K = R regions)
+        mbar_wait(bar(UD_READY), ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_bf16_w(tmem + cDGV, loUD1m + ((ks * 512) >> 4), hi32, loU1m + ((ks * 512) >> 4), hi32, idDGV,
+                       !(first_of_video && ks == 0));
+#pragma unroll
+          for (int ks = 0; ks < NC; ++ks)
+            mma_bf16_w(tmem + cDGT, loUD2k + ((ks * kCh32) >> 4), hi32, loU2k + ((ks * kCh32) >> 4), hi32, idDGT, ks != 0);
+          tc_commit(bar(DG_DONE));
+        }
+        __syncwarp();
+        if (++jt == tpv) jt = 0;
+        if (k + 1 < n_tiles) issue_S(k + 1, jt == 0);
+      }
+    } else if (warp == 2) {
+      // ================= P stores: the bf16 gradient tile of each unit leaves through TMA =================
+      if (lane == 0) {
+        for (int k = 0; k < n_tiles; ++k) {
+          mbar_wait(bar(P_READY), k & 1);
+          const int row = (int)((u0 + k) * kRows);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) tma_store_2d(&mapP, sbase + L::U1 + c * kCh32, c * 16, row);
+          bulk_commit();
+          bulk_wait_read0();                 // the staging tile may be overwritten (next tile's U1)
+          mbar_arrive(bar(P_STORED));
+        }
+        bulk_wait_all();
+      }
+    }
+  } else {
+    // ============================ compute warps ============================
+    if (NC == 5) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    const int cw = warp - 4;
+    const int g = cw >> 2, q = cw & 3;          // column chunk, text slot / TMEM lane quadrant
+    const int m = q * 32 + lane;                // word row of the tile
+    const int cl = lane & 15;                   // table column handled by this lane
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t sw = (uint32_t)((m >> 2) & 1) << 4;
+    const uint32_t row_off = (uint32_t)g * kCh32 + (uint32_t)m * 32;
+    const uint32_t seg0 = row_off + sw, seg1 = row_off + (16u ^ sw);
+    float4* tab = reinterpret_cast<float4*>(sgen + L::TAB + cw * 768);
+    const float4* s_rowv = reinterpret_cast<const float4*>(sgen + L::ROWV);
+    const float4* s_colv = reinterpret_cast<const float4*>(sgen + L::COLV);
+    const float* s_beta = reinterpret_cast<const float*>(sgen + L::BETA);
+    const float* s_m2t = reinterpret_cast<const float*>(sgen + L::M2T);
+    const float* s_alpha = reinterpret_cast<const float*>(sgen + L::ALPHA);
+    const float* s_m2v = reinterpret_cast<const float*>(sgen + L::M2V);
+    float* s_tbp = reinterpret_cast<float*>(sgen + L::TBP);
+    int vloads = 0, i = i0, jt = jt0;
+    for (int k = 0; k < n_tiles; ++k) {
+      const uint32_t ph = k & 1;
+      const int j = jt * kTPT + q;
+      const bool last_of_video = (k == n_tiles - 1) || (jt == tpv - 1);
+      const float gs = j < a.Bt ? __ldg(a.d_scores + (size_t)i * a.Bt + j) : 0.f;
+      if (k == 0 || jt == 0) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
+      mbar_wait(bar(VEC_FULL), ph);
+      // ---- per-row scalars (this thread's word) and the per-column tables of this warp's 16 regions
+      const float4 rv = s_rowv[m];              // nB, thr1, rden1, cos1
+      const float beta_m = s_beta[m], m2t_m = s_m2t[m];
+      float nA_cl;
+      {
+        const int r = g * 16 + cl;
+        const float4 cv = s_colv[q * R + r];    // nA, thr2, rden2, cos2
+        const float al = s_alpha[r], mv = s_m2v[r];
+        const float c1B = gs * (1.f / R) * cv.z, kapB = cv.w * cv.z;
+        nA_cl = cv.x;
+        if (lane < 16) {
+          tab[cl] = make_float4(cv.x, cv.y, al, mv);
+          tab[16 + cl] = make_float4(a.lam * c1B, kapB, -0.5f * c1B * kapB, cv.x);
+          tab[32 + cl] = make_float4(0.f, c1B, al, 0.f);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(VEC_FREE));
+      const float nB = rv.x, thr1 = rv.y;
+      const float c1A = gs * (1.f / kW) * rv.z, kapA = rv.w * rv.z;
+      const float dDA = -0.5f * c1A * kapA, lc1A = a.lam * c1A;
+
+      // ------------------------------ phase 1: recompute u1, u2 ------------------------------
+      mbar_wait(bar(S_DONE), ph);
+      tc_fence_after();
+      float x[16];
+      tmem_ld16(tmem + cS + lane_off + g * 16, reinterpret_cast<uint32_t*>(x));
+      tmem_ld_wait();
+      uint32_t ub[16];                          // lo = u1 (i2t), hi = u2 (t2i), bf16 as the MMAs see them
+      {
+        const float nBl = nB * a.lam2;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float4 t1 = tab[c];
+          x[c] *= t1.z * beta_m;
+          const float l = leaky(x[c]);
+          const float eA = ex2(fmaf(l * t1.x, a.lam2, t1.w));
+          const float eB = ex2(fmaf(l, nBl, m2t_m));
+          ub[c] = pack_bf16(eA > thr1 ? eA : 0.f, eB > t1.y ? eB : 0.f);
+        }
+      }
+      if (k > 0) mbar_wait(bar(P_STORED), (k - 1) & 1);     // the TMA store of tile k-1 has read the U1 buffer
+      st_shared_v4(sbase + L::U1 + seg0, prmt(ub[0], ub[1], 0x5410), prmt(ub[2], ub[3], 0x5410), prmt(ub[4], ub[5], 0x5410),
+                   prmt(ub[6], ub[7], 0x5410));
+      st_shared_v4(sbase + L::U1 + seg1, prmt(ub[8], ub[9], 0x5410), prmt(ub[10], ub[11], 0x5410),
+                   prmt(ub[12], ub[13], 0x5410), prmt(ub[14], ub[15], 0x5410));
+      st_shared_v4(sbase + L::U2 + seg0, prmt(ub[0], ub[1], 0x7632), prmt(ub[2], ub[3], 0x7632), prmt(ub[4], ub[5], 0x7632),
+                   prmt(ub[6], ub[7], 0x7632));
+      st_shared_v4(sbase + L::U2 + seg1, prmt(ub[8], ub[9], 0x7632), prmt(ub[10], ub[11], 0x7632),
+                   prmt(ub[12], ub[13], 0x7632), prmt(ub[14], ub[15], 0x7632));
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(U_READY));
+
+      // ---------------- phase 2: dA of both directions, UD = u dD, l2-norm backward sums ----------------
+      mbar_wait(bar(Y_DONE), ph);
+      tc_fence_after();
+      float Q[16];                              // dA1 nA + dA2 nB
+      float tB = 0.f;
+      float tA;
+      {
+        // i2t direction.  Columns are visited as (c, c+1, c+8, c+9) so that the first butterfly step of the
+        // lanes->columns reduction of A1 dA1 can be folded in immediately (8 live partials instead of 16).
+        float y[16], p8[8];
+        uint32_t d1[8];
+        tmem_ld16(tmem + cY1 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
+        tmem_ld_wait();
+        const bool up8 = (lane & 8) != 0;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          float a1[4], pa[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int cc = c + (h & 1) + (h >> 1) * 8;
+            const float4 t2 = tab[16 + cc];     // lambda c1B, kapB, dDB, nA
+            const float xv = x[cc];
+            const float uA = bf16_lo(ub[cc]);
+            const float dAA = lc1A * uA * fmaf(-kapA, y[cc], xv);
+            const float E = dAA * t2.w;
+            Q[cc] = E;
+            pa[h] = leaky(xv) * E;
+            a1[h] = uA * dDA;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float send = up8 ? pa[h] : pa[h + 2];
+            const float keep = up8 ? pa[h + 2] : pa[h];
+            p8[c + h] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          d1[c >> 1] = pack_bf16(a1[0], a1[1]);
+          d1[(c >> 1) + 4] = pack_bf16(a1[2], a1[3]);
+        }
+        st_shared_v4(sbase + L::UD1 + seg0, d1[0], d1[1], d1[2], d1[3]);
+        st_shared_v4(sbase + L::UD1 + seg1, d1[4], d1[5], d1[6], d1[7]);
+        // t_A[text, region] = sum over the 32 words of this text of A1 dA1: lane l ends with column l & 15
+#pragma unroll
+        for (int h = 4; h >= 1; h >>= 1) {
+          const bool up = (lane & h) != 0;
+#pragma unroll
+          for (int e = 0; e < h; ++e) {
+            const float send = up ? p8[e] : p8[e + h];
+            const float keep = up ? p8[e + h] : p8[e];
+            p8[e] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+          }
+        }
+        tA = p8[0] + __shfl_xor_sync(0xffffffffu, p8[0], 16);
+      }
+      {
+        // t2i direction
+        float y[16];
+        uint32_t d2[8];
+        tmem_ld16(tmem + cY2 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          float a2[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = c + h;
+            const float4 t2 = tab[16 + cc];
+            const float xv = x[cc];
+            const float uB = bf16_hi(ub[cc]);
+            const float dAB = t2.x * uB * fmaf(-t2.y, y[cc], xv);
+            const float F = dAB * nB;
+            tB = fmaf(leaky(xv), F, tB);
+            Q[cc] += F;
+            a2[h] = uB * t2.z;
+          }
+          d2[c >> 1] = pack_bf16(a2[0], a2[1]);
+        }
+        st_shared_v4(sbase + L::UD2 + seg0, d2[0], d2[1], d2[2], d2[3]);
+        st_shared_v4(sbase + L::UD2 + seg1, d2[4], d2[5], d2[6], d2[7]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(UD_READY));
+      s_tbp[g * kRows + m] = tB;
+      if (lane < 16) reinterpret_cast<float*>(tab + 32 + cl)[0] = nA_cl * nA_cl * tA;
+      named_bar_sync(1 + q, 32 * NC);           // the NC warps that share this text slot
+      float zB = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < NC; ++gg) zB += s_tbp[gg * kRows + m];
+      zB *= nB * nB;
+
+      // ------------------------------ phase 3: dS, P ------------------------------
+      uint32_t pk[8];
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        float pv[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cc = c + h;
+          const float4 t3 = tab[32 + cc];       // nA^2 tA, c1B, alpha
+          const float xv = x[cc], l = leaky(xv);
+          const float uA = bf16_lo(ub[cc]), uB = bf16_hi(ub[cc]);
+          const float dS = leaky_grad(xv) * fmaf(-l, t3.x + zB, Q[cc]) + fmaf(c1A, uA, t3.y * uB);
+          pv[h] = dS * (t3.z * beta_m);
+        }
+        pk[c >> 1] = pack_bf16(pv[0], pv[1]);
+      }
+      mbar_wait(bar(DG_DONE), ph);              // the dG GEMMs have consumed U1 / U2: U1 takes P
+      st_shared_v4(sbase + L::U1 + seg0, pk[0], pk[1], pk[2], pk[3]);
+      st_shared_v4(sbase + L::U1 + seg1, pk[4], pk[5], pk[6], pk[7]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(P_READY));
+
+      // ------------------------------ Gram gradients leave TMEM ------------------------------
+      tc_fence_after();
+      if (g < 2) {
+        // dG^T block of this text (rows = this word), 16 of its 32 columns per warpgroup
+        float v[16];
+        tmem_ld16(tmem + cDGT + lane_off + q * 32 + g * 16, reinterpret_cast<uint32_t*>(v));
+        tmem_ld_wait();
+        if (j < a.Bt) {
+          float* dst = a.dgt + ((size_t)jt * kRows + m) * kW + g * 16;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) red_add_v4(dst + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+      }
+      if (last_of_video && q * 32 < R) {
+        // dG^V rows (TMEM lanes = regions), this warpgroup's 16 columns
+        float v[16];
+        tmem_ld16(tmem + cDGV + lane_off + g * 16, reinterpret_cast<uint32_t*>(v));
+        tmem_ld_wait();
+        if (m < R) {
+          float* dst = a.dgv + ((size_t)i * R + m) * R + g * 16;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) red_add_v4(dst + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+      }
+      tc_fence_before();
+      if (++jt == tpv) { jt = 0; ++i; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// bf16 matrix (rows x cols, row-major) -> boxes of box_cols x box_rows, 128- or 32-byte swizzle
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                    CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return DVLP_ERR_CUDA;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return DVLP_ERR_CUDA; }
+  return DVLP_OK;
+}
+
+template <int R>
+static int launch(const void* vb, const void* tb, int Bv, int Bt, float lambda, const float* d_scores, char* ws,
+                  const Workspace& Lw, cudaStream_t st) {
+  using L = Lay<R>;
+  CUtensorMap mV, mT, mGV, mGBD, mP;
+  int rc;
+  Args a{};
+  a.Bv = Bv; a.Bt = Bt;
+  a.tiles_per_video = (Bt + kTPT - 1) / kTPT;
+  a.total_units = (long long)Bv * a.tiles_per_video;
+  if ((rc = make_map(&mV, vb, (uint64_t)Bv * R, kD, R, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&mT, tb, (uint64_t)Bt * kW, kD, kRows, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&mGV, ws + Lw.gvb, (uint64_t)Bv * R, R, R, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&mGBD, ws + Lw.gbd, (uint64_t)a.tiles_per_video * kRows, kRows, kRows, 64, CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  // P spill: [unit][128 words][R regions] bf16, one 16-column box per chunk
+  if ((rc = make_map(&mP, ws + Lw.pa, (uint64_t)a.total_units * kRows, R, kRows, 16, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  a.alpha = (const float*)(ws + Lw.alpha); a.beta = (const float*)(ws + Lw.beta);
+  a.m2v = (const float*)(ws + Lw.m2v); a.m2t = (const float*)(ws + Lw.m2t);
+  a.d_scores = d_scores;
+  a.rowv = (const float4*)(ws + Lw.rowv); a.colv = (const float4*)(ws + Lw.colv);
+  a.lam = lambda; a.lam2 = lambda * kLog2e;
+  a.dgv = (float*)(ws + Lw.dgv); a.dgt = (float*)(ws + Lw.dgt);
+  int dev = 0, sms = 148;
+  DVLP_CUDA_OK(cudaGetDevice(&dev));
+  DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int grid = (int)(a.total_units < sms ? a.total_units : sms);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_pair_bwd2<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
+    attr_set = true;
+  }
+  k_pair_bwd2<R><<<grid, L::kThreads, L::kAlloc, st>>>(mV, mT, mGV, mGBD, mP, a);
+  DVLP_LAUNCH_OK();
+  return DVLP_OK;
+}
+}  // namespace tb2
+
+int run_pair_bwd2(const void* vb, const void* tb, int Bv, int Bt, int R, int W, int d, float lambda,
+                  const float* d_scores, char* ws, const Workspace& L, cudaStream_t st) {
+  if (d != tb2::kD || W != tb2::kW) return DVLP_ERR_BAD_SHAPE;
+  switch (R) {
+    case 80: return tb2::launch<80>(vb, tb, Bv, Bt, lambda, d_scores, ws, L, st);
+    case 64: return tb2::launch<64>(vb, tb, Bv, Bt, lambda, d_scores, ws, L, st);
+    case 48: return tb2::launch<48>(vb, tb, Bv, Bt, lambda, d_scores, ws, L, st);
+    case 32: return tb2::launch<32>(vb, tb, Bv, Bt, lambda, d_scores, ws, L, st);
+  }
+  return DVLP_ERR_BAD_SHAPE;
+}
+
+}  // namespace dvlp

@@ -66,6 +66,7 @@ struct Args {
   int focal;
   float* scores;
   float *nrm_a, *nrm_b;   // per unit: [4][R] and [128] attention l2-norm factors, kept for the backward
+  float4 *rowv, *colv;    // per unit: per-word / per-(text, region) query scalars for pair_bwd2.cu (see common.cuh)
 };
 
 template <int R>
@@ -234,6 +235,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       // pass 1: S = raw * alpha_r * beta_w ; |LeakyReLU(S)|^2 over regions = this word's dir-B norm
       // (4 independent accumulators: the chains are latency-, not throughput-bound at 2 warps/scheduler)
       float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+      float inb;
 #pragma unroll
       for (int r = 0; r < R; r += 4) {
         const float4 al = *reinterpret_cast<const float4*>(s_alpha + r);
@@ -242,7 +244,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
         for (int h = 0; h < 4; ++h) { float l = leaky(S[r + h]); acc4[h] = fmaf(l, l, acc4[h]); }
       }
       {
-        const float inb = 1.f / (sqrtf((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + kEps);
+        inb = 1.f / (sqrtf((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + kEps);
         s_invnB[m] = inb;
         a.nrm_b[(size_t)(u0 + k) * kRows + m] = inb;
       }
@@ -297,7 +299,9 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
 #pragma unroll
         for (int h = 0; h < 4; ++h) d4[h] = fmaf(e[r + h], S[r + h], d4[h]);
       const float Dn = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-      float cs = Dn > 1e-30f ? num * rsqrtf(Dn) : 0.f;
+      const float rden = Dn > 1e-30f ? rsqrtf(Dn) : 0.f;
+      float cs = num * rden;
+      a.rowv[(size_t)(u0 + k) * kRows + m] = make_float4(inb, thr, rden, cs);
       cs = warp_sum(cs);                      // mean over the 32 words of text q (model/loss.py:318)
       named_bar_sync(2, kGroup);              // group B's per-text partial sums are in s_part
       if (lane == 0 && j < a.Bt) {
@@ -327,7 +331,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
       const float* beta = s_beta + set * 128;
       const float* m2t = s_m2t + set * 128;
       const uint32_t tS2 = tmem + set * 256 + 128 + lane_off;
-      float num[2];
+      float num[2], inav[2], thrv[2];
       if (warp_active) {
         // pass 1: per text, |LeakyReLU(S)|^2 over its 32 words = this region's dir-A norm
 #pragma unroll
@@ -347,8 +351,9 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             s4[2] = fmaf(l2, l2, s4[2]); s4[3] = fmaf(l3, l3, s4[3]);
           }
           const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          const float ina = 1.f / (sqrtf(ss) + kEps);
+          inav[tt] = ina;
           if (active) {
-            const float ina = 1.f / (sqrtf(ss) + kEps);
             s_invnA[t * R + r] = ina;
             a.nrm_a[((size_t)(u0 + k) * kTPT + t) * R + r] = ina;
           }
@@ -378,6 +383,7 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             for (int h = 0; h < 4; ++h) e4[h] += e[w + h];
           }
           const float thr = a.focal ? ((e4[0] + e4[1]) + (e4[2] + e4[3])) * (1.f / kW) : -1.f;
+          thrv[tt] = thr;
           float n4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -422,7 +428,9 @@ k_pair_tc_fwd(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ 
             }
           }
           const float Dn = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-          cs[tt] = (active && Dn > 1e-30f) ? num[tt] * rsqrtf(Dn) : 0.f;
+          const float rden = (active && Dn > 1e-30f) ? rsqrtf(Dn) : 0.f;
+          cs[tt] = active ? num[tt] * rden : 0.f;
+          if (active) a.colv[((size_t)(u0 + k) * kTPT + t) * R + r] = make_float4(inav[tt], thrv[tt], rden, cs[tt]);
         }
       }
       tc_fence_before();
@@ -490,6 +498,7 @@ static int launch_fwd(const void* vb, const void* tb, int Bv, int Bt, float lamb
   a.m2v = (const float*)(ws + Lw.m2v); a.m2t = (const float*)(ws + Lw.m2t);
   a.lam2 = lambda * kLog2e; a.focal = focal; a.scores = scores;
   a.nrm_a = (float*)(ws + Lw.nrm_a); a.nrm_b = (float*)(ws + Lw.nrm_b);
+  a.rowv = (float4*)(ws + Lw.rowv); a.colv = (float4*)(ws + Lw.colv);
   int dev = 0, sms = 148;
   DVLP_CUDA_OK(cudaGetDevice(&dev));
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -774,6 +774,16 @@ bool tc_bwd_available() {
   return on == 1;
 }
 
+// DVLP_TC_BWD=1: first tcgen05 backward (this file + grad_gemm.cu); default 2: pair_bwd2.cu + grad_gemm2.cu
+int tc_bwd_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVLP_TC_BWD");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 int run_pair_tc_bwd(const void* vb, const void* tb, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
                     const float* d_scores, char* ws, const Workspace& L, cudaStream_t st) {
   if (d != tcb::kD || W != tcb::kW) return DVLP_ERR_BAD_SHAPE;

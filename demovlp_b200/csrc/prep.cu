@@ -142,12 +142,15 @@ __global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restri
                                                    float* __restrict__ mterm_v, float* __restrict__ mterm_t,
                                                    float* __restrict__ m2v, float* __restrict__ m2t,
                                                    __nv_bfloat16* __restrict__ gvb, __nv_bfloat16* __restrict__ gtb,
-                                                   int pad_from, int pad_to) {
+                                                   __nv_bfloat16* __restrict__ gbd, int pad_from, int pad_to) {
   extern __shared__ __align__(16) uint8_t psm[];
   __shared__ float s_inv[128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if ((int)blockIdx.x == Bv + Bt) {            // padded tail of beta / m2t (whole 128-row tiles are bulk-copied)
     for (int e = pad_from + threadIdx.x; e < pad_to; e += blockDim.x) { beta[e] = 0.f; m2t[e] = 0.f; }
+    // rows of the missing texts in the last block-diagonal Gram tile
+    if (gbd)
+      for (int e = pad_from * 128 + threadIdx.x; e < pad_to * 128; e += blockDim.x) gbd[e] = __float2bfloat16(0.f);
     return;
   }
   const bool text = (int)blockIdx.x >= Bv;
@@ -159,6 +162,13 @@ __global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restri
   float* mt = (text ? mterm_t : mterm_v) + (size_t)item * L;
   float* m2 = (text ? m2t : m2v) + (size_t)item * L;
   __nv_bfloat16* G = (text ? gtb : gvb) + (size_t)item * L * L;
+  // block-diagonal copy of the text Gram matrix (W == 32): rows item*32.. of a (tiles*128) x 128 matrix,
+  // this text's 32 x 32 block at columns (item % 4) * 32, zeros elsewhere (pair_bwd2.cu: Y2 = Gbd U2)
+  __nv_bfloat16* Gd = (text && gbd) ? gbd + (size_t)item * 32 * 128 : nullptr;
+  const int dcol = (item & 3) * 32;
+  if (Gd)
+    for (int e = threadIdx.x; e < 32 * 128; e += blockDim.x)
+      if (((e & 127) >> 5) != (item & 3)) Gd[e] = __float2bfloat16(0.f);
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(psm);
   // stage rows (16-byte chunks: 32 per row)
   for (int e = threadIdx.x; e < L * 32; e += blockDim.x) {
@@ -216,9 +226,14 @@ __global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restri
         const int r = ti * 16 + g + half * 8, c = tj * 16 + h * 8 + tq * 2;
         const float x0 = acc[h][half * 2] * s_inv[r] * s_inv[c], x1 = acc[h][half * 2 + 1] * s_inv[r] * s_inv[c + 1];
         *reinterpret_cast<__nv_bfloat162*>(G + (size_t)r * L + c) = __floats2bfloat162_rn(x0, x1);
+        if (Gd) *reinterpret_cast<__nv_bfloat162*>(Gd + (size_t)r * 128 + dcol + c) = __floats2bfloat162_rn(x0, x1);
         if (tj != ti) {
           G[(size_t)c * L + r] = __float2bfloat16(x0);
           G[(size_t)(c + 1) * L + r] = __float2bfloat16(x1);
+          if (Gd) {
+            Gd[(size_t)c * 128 + dcol + r] = __float2bfloat16(x0);
+            Gd[(size_t)(c + 1) * 128 + dcol + r] = __float2bfloat16(x1);
+          }
         }
       }
   }
@@ -297,7 +312,8 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
     const bool pad = nt_pad > (size_t)Bt * W;
     k_prep_item<<<Bv + Bt + (pad ? 1 : 0), 256, smem, st>>>(
         vb, tb, im_mask, s_mask, Bv, Bt, R, W, lambda, alpha, beta, mv, mt, (float*)(ws + L.m2v), (float*)(ws + L.m2t),
-        (__nv_bfloat16*)(ws + L.gvb), (__nv_bfloat16*)(ws + L.gtb), Bt * W, (int)nt_pad);
+        (__nv_bfloat16*)(ws + L.gvb), (__nv_bfloat16*)(ws + L.gtb), W == 32 ? (__nv_bfloat16*)(ws + L.gbd) : nullptr, Bt * W,
+        (int)nt_pad);
     DVLP_LAUNCH_OK();
     return DVLP_OK;
   }
