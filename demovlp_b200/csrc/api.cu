@@ -39,7 +39,7 @@ int run_pair_generic(bool backward, const PairArgs& a, int n_cta, cudaStream_t s
 int run_grad_finalize(const void*, int, const float*, const float*, const float*, int, int, int, int, float*,
                       cudaStream_t);
 int run_grad_finalize_tc(const void*, const void*, const float*, const float*, const float*, const float*, const float*,
-                         const float*, int, int, int, int, float*, float*, cudaStream_t);
+                         const float*, int, int, int, int, int, float*, float*, cudaStream_t);
 int run_rwa_loss(const float*, int, int, int, int, float, float*, float*, cudaStream_t);
 int run_normsoftmax(const float*, int, int, float, float*, float*, float*, cudaStream_t);
 int run_sim_fwd(const void*, const void*, int, int, int, float, int, float*, float*, cudaStream_t);
@@ -248,7 +248,7 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   cudaStream_t st = (cudaStream_t)stream;
   // zero the accumulators (one contiguous range: dvh .. dgt)
   DVLP_CUDA_OK(cudaMemsetAsync(ws + L.dvh, 0, L.pa - L.dvh, st));
-  int prescaled = 0;
+  int prescaled = 0, dgt_swz = 0;
   {
   ProfScope p(kProfBwd, st);
   if (tc && tc_bwd_available()) {
@@ -257,6 +257,7 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
     if (tc_bwd_version() == 2) {
       if ((rc = run_pair_bwd2(vb, tb, Bv, Bt, R, W, d, lambda, d_scores, ws, L, st))) return rc;
       if ((rc = run_grad_gemm2(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
+      dgt_swz = 1;
     } else {
       if ((rc = run_pair_tc_bwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, d_scores, ws, L, st))) return rc;
       if ((rc = run_grad_gemm(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
@@ -282,7 +283,7 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   if (prescaled && d == 256 && (R % 16) == 0 && (W % 16) == 0 && R <= 128 && W <= 128)
     return run_grad_finalize_tc(xv, xt, (const float*)(ws + L.alpha), (const float*)(ws + L.beta),
                                 (const float*)(ws + L.dvh), (const float*)(ws + L.dth), (const float*)(ws + L.dgv),
-                                (const float*)(ws + L.dgt), Bv, Bt, R, W, d_im, d_s, st);
+                                (const float*)(ws + L.dgt), Bv, Bt, R, W, dgt_swz, d_im, d_s, st);
   if ((rc = run_grad_finalize(xv, xdt, (const float*)(ws + L.alpha), (const float*)(ws + L.dvh),
                               (const float*)(ws + L.dgv), Bv, R, d, prescaled, d_im, st)))
     return rc;

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __re
                                                        const float* __restrict__ alpha, const float* __restrict__ beta,
                                                        const float* __restrict__ dvh, const float* __restrict__ dth,
                                                        const float* __restrict__ dgv, const float* __restrict__ dgt,
-                                                       int Bv, int R, int W, float* __restrict__ d_im, float* __restrict__ d_s) {
+                                                       int Bv, int R, int W, int dgt_swz, float* __restrict__ d_im,
+                                                       float* __restrict__ d_s) {
   extern __shared__ __align__(16) uint8_t fsm[];
   __shared__ float s_inv[128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,7 +155,9 @@ __global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __re
   __syncthreads();
   for (int e = threadIdx.x; e < L * L / 2; e += blockDim.x) {
     const int r = (2 * e) / L, c = 2 * e - r * L;
-    const float2 g = *reinterpret_cast<const float2*>(dG + (size_t)r * L + c);
+    // pair_bwd2.cu leaves dG^T rows (W == 32) with their 16-byte chunks XOR-swizzled by the row index
+    const int cs = (text && dgt_swz) ? ((((c >> 2) ^ (r & 7)) << 2) | (c & 3)) : c;
+    const float2 g = *reinterpret_cast<const float2*>(dG + (size_t)r * L + cs);
     const float sr = 2.f * s_inv[r];
     *reinterpret_cast<__nv_bfloat162*>(as + r * ldA + c * 2) = __floats2bfloat162_rn(g.x * sr * s_inv[c], g.y * sr * s_inv[c + 1]);
   }
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __re
 
 // both sides in one launch (tcgen05 path)
 int run_grad_finalize_tc(const void* v, const void* t, const float* alpha, const float* beta, const float* dvh,
-                         const float* dth, const float* dgv, const float* dgt, int Bv, int Bt, int R, int W,
+                         const float* dth, const float* dgv, const float* dgt, int Bv, int Bt, int R, int W, int dgt_swz,
                          float* d_im, float* d_s, cudaStream_t st) {
   const int Lmax = R > W ? R : W;
   const size_t smem = (size_t)Lmax * kFinLdX + (size_t)Lmax * (Lmax + 8) * 2;
@@ -222,7 +225,7 @@ int run_grad_finalize_tc(const void* v, const void* t, const float* alpha, const
     attr_set = true;
   }
   k_finalize_item<<<Bv + Bt, 256, smem, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)t, alpha, beta, dvh, dth,
-                                              dgv, dgt, Bv, R, W, d_im, d_s);
+                                              dgv, dgt, Bv, R, W, dgt_swz, d_im, d_s);
   DVLP_LAUNCH_OK();
   return DVLP_OK;
 }

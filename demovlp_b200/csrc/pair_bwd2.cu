@@ -33,6 +33,8 @@
 namespace dvlp {
 using namespace ptx;
 
+extern void* g_trace_buffer;   // pair_tc_bwd.cu (dvlp_debug_set_trace)
+
 namespace tb2 {
 constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128;
 constexpr int kTileBytes = 16384;   // 128 rows x 128 B (one 64-column chunk of a 128-byte-swizzle tile)
@@ -66,7 +68,7 @@ struct Lay {
   static_assert(kAlloc <= 232448, "shared memory budget");
 };
 
-enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE, U_READY, Y_DONE, UD_READY, DG_DONE, P_READY,
+enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE, U_READY, Y_DONE, DGT_STAGED, DG_DONE, P_READY,
            P_STORED, kNumBars };
 
 // TMEM columns
@@ -79,7 +81,14 @@ struct Args {
   const float4 *rowv, *colv;     // per-unit scalars saved by the forward kernel
   float lam, lam2;
   float *dgv, *dgt;
+  long long* trace;   // debug: per-phase clock64 stamps of CTA 0 (tools/trace_tiles.py), NULL in production
 };
+// trace slot layout: [role 0..4][tile 0..31][event 0..15]; roles: 1 = MMA warp, 2 = compute warp (g0,q0), 3 = (g4,q3)
+#define TR2(role, ev)                                                                        \
+  do {                                                                                      \
+    if (a.trace && blockIdx.x == 0 && lane == 0 && k < 32) a.trace[((role) * 32 + k) * 16 + (ev)] = clock64(); \
+  } while (0)
+#define TRC(ev) do { if (cw == 0) TR2(2, ev); else if (cw == NW - 1) TR2(3, ev); } while (0)
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -133,7 +142,8 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     prefetch_tmap(&mapV); prefetch_tmap(&mapT); prefetch_tmap(&mapGV); prefetch_tmap(&mapGBD); prefetch_tmap(&mapP);
     for (int b = 0; b < kNumBars; ++b) {
       uint32_t cnt = 1;
-      if (b == VEC_FREE || b == U_READY || b == UD_READY || b == P_READY) cnt = NW;
+      if (b == VEC_FREE || b == U_READY || b == P_READY) cnt = NW;
+      if (b == DGT_STAGED) cnt = 8;
       mbar_init(bar(b), cnt);
     }
     fence_mbar_init();
@@ -163,14 +173,14 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           bulk_load(sbase + L::COLV, a.colv + unit * (kTPT * R), 4 * R * 16, bar(VEC_FULL));
           bulk_load(sbase + L::BETA, a.beta + (size_t)jt * kRows, 512, bar(VEC_FULL));
           bulk_load(sbase + L::M2T, a.m2t + (size_t)jt * kRows, 512, bar(VEC_FULL));
-          // block-diagonal text Gram tile: the Y2 GEMM of the previous tile has read it
-          if (k > 0) mbar_wait(bar(Y_DONE), pp);
-          mbar_arrive_expect_tx(bar(GBD_FULL), 2 * kTileBytes);
-          for (int c = 0; c < 2; ++c) tma_load_2d(sbase + L::GBD + c * kTileBytes, &mapGBD, c * 64, jt * kRows, bar(GBD_FULL));
           // text tile: its buffer doubles as UD1 / UD2 until the dG GEMMs of the previous tile are done
           if (k > 0) mbar_wait(bar(DG_DONE), pp);
           mbar_arrive_expect_tx(bar(T_FULL), 4 * kTileBytes);
           for (int c = 0; c < 4; ++c) tma_load_2d(sbase + L::T + c * kTileBytes, &mapT, c * 64, jt * kRows, bar(T_FULL));
+          // block-diagonal text Gram tile: its buffer staged the dG^T block of the previous tile (bulk reduce read it)
+          if (k > 0) mbar_wait(bar(P_STORED), pp);
+          mbar_arrive_expect_tx(bar(GBD_FULL), 2 * kTileBytes);
+          for (int c = 0; c < 2; ++c) tma_load_2d(sbase + L::GBD + c * kTileBytes, &mapGBD, c * 64, jt * kRows, bar(GBD_FULL));
           if (k == 0 || jt == 0) {
             // the resident video changes: everybody is done with tile k-1
             if (k > 0) mbar_wait(bar(P_READY), pp);
@@ -217,6 +227,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         mbar_wait(bar(GBD_FULL), ph);
         mbar_wait(bar(U_READY), ph);
         tc_fence_after();
+        TR2(1, 0);
         if (lane == 0) {
 #pragma unroll
           for (int ks = 0; ks < NC; ++ks)
@@ -229,9 +240,8 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           tc_commit(bar(Y_DONE));
         }
         __syncwarp();
-        // ---- dGV += UD1^T U1 (K = 128 words),  dGT = UD2 U2^T (K = R regions)
-        mbar_wait(bar(UD_READY), ph);
-        tc_fence_after();
+        // ---- dGV += UD1^T U1 (K = 128 words),  dGT = UD2 U2^T (K = R regions): UD was written with U
+        TR2(1, 1);
         if (lane == 0) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
@@ -243,20 +253,30 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           tc_commit(bar(DG_DONE));
         }
         __syncwarp();
+        TR2(1, 3);
         if (++jt == tpv) jt = 0;
         if (k + 1 < n_tiles) issue_S(k + 1, jt == 0);
+        TR2(1, 4);
       }
     } else if (warp == 2) {
-      // ================= P stores: the bf16 gradient tile of each unit leaves through TMA =================
+      // ====== stores: the bf16 gradient tile P of each unit (TMA tile store) and its dG^T block (bulk add) ======
       if (lane == 0) {
+        int jt = jt0;
         for (int k = 0; k < n_tiles; ++k) {
           mbar_wait(bar(P_READY), k & 1);
           const int row = (int)((u0 + k) * kRows);
 #pragma unroll
           for (int c = 0; c < NC; ++c) tma_store_2d(&mapP, sbase + L::U1 + c * kCh32, c * 16, row);
           bulk_commit();
-          bulk_wait_read0();                 // the staging tile may be overwritten (next tile's U1)
+          // dG^T: 128 rows x 32 fp32 staged row-major in the (idle) Gbd buffer; only the rows of real texts are added
+          mbar_wait(bar(DGT_STAGED), k & 1);
+          int nt = a.Bt - jt * kTPT;
+          nt = nt > kTPT ? kTPT : nt;
+          bulk_reduce_add_f32(a.dgt + (size_t)jt * kRows * kW, sbase + L::GBD, (uint32_t)nt * kW * kW * 4);
+          bulk_commit();
+          bulk_wait_read0();                 // U1 may take the next tile's u, the Gbd buffer the next Gram tile
           mbar_arrive(bar(P_STORED));
+          if (++jt == tpv) jt = 0;
         }
         bulk_wait_all();
       }
@@ -281,13 +301,23 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     const float* s_m2v = reinterpret_cast<const float*>(sgen + L::M2V);
     float* s_tbp = reinterpret_cast<float*>(sgen + L::TBP);
     int vloads = 0, i = i0, jt = jt0;
+    auto load_g = [&](int vi, int tj) {         // d_scores of this warp's (video, text); 0 for a padded text
+      const int jj = tj * kTPT + q;
+      float v = 0.f;
+      if (jj < a.Bt) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(a.d_scores + (size_t)vi * a.Bt + jj));
+      return v;
+    };
+    float gs_next = load_g(i, jt);
     for (int k = 0; k < n_tiles; ++k) {
       const uint32_t ph = k & 1;
       const int j = jt * kTPT + q;
       const bool last_of_video = (k == n_tiles - 1) || (jt == tpv - 1);
-      const float gs = j < a.Bt ? __ldg(a.d_scores + (size_t)i * a.Bt + j) : 0.f;
+      const float gs = gs_next;
+      if (k + 1 < n_tiles) gs_next = (jt + 1 == tpv) ? load_g(i + 1, 0) : load_g(i, jt + 1);   // one tile ahead
+      TRC(0);
       if (k == 0 || jt == 0) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
       mbar_wait(bar(VEC_FULL), ph);
+      TRC(1);
       // ---- per-row scalars (this thread's word) and the per-column tables of this warp's 16 regions
       const float4 rv = s_rowv[m];              // nB, thr1, rden1, cos1
       const float beta_m = s_beta[m], m2t_m = s_m2t[m];
@@ -299,26 +329,27 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         const float c1B = gs * (1.f / R) * cv.z, kapB = cv.w * cv.z;
         nA_cl = cv.x;
         if (lane < 16) {
-          tab[cl] = make_float4(cv.x, cv.y, al, mv);
-          tab[16 + cl] = make_float4(a.lam * c1B, kapB, -0.5f * c1B * kapB, cv.x);
-          tab[32 + cl] = make_float4(0.f, c1B, al, 0.f);
+          tab[cl] = make_float4(cv.x, cv.y, al, mv);                          // phase 1: nA, thr2, alpha, m2v
+          tab[16 + cl] = make_float4(a.lam * c1B, kapB, cv.x, c1B);          // phase 2: lambda c1B, kapB, nA, c1B
+          tab[32 + cl] = make_float4(0.f, al, -0.5f * c1B * kapB, 0.f);      // phase 3: nA^2 tA, alpha | phase 1: dDB
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(VEC_FREE));
-      const float nB = rv.x, thr1 = rv.y;
+      const float nB = rv.x;
       const float c1A = gs * (1.f / kW) * rv.z, kapA = rv.w * rv.z;
-      const float dDA = -0.5f * c1A * kapA, lc1A = a.lam * c1A;
+      const float lc1A = a.lam * c1A;
 
-      // ------------------------------ phase 1: recompute u1, u2 ------------------------------
+      // -------------- phase 1: recompute u1, u2; U = u and UD = u dD operand tiles --------------
       mbar_wait(bar(S_DONE), ph);
       tc_fence_after();
+      TRC(2);
       float x[16];
       tmem_ld16(tmem + cS + lane_off + g * 16, reinterpret_cast<uint32_t*>(x));
       tmem_ld_wait();
       uint32_t ub[16];                          // lo = u1 (i2t), hi = u2 (t2i), bf16 as the MMAs see them
       {
-        const float nBl = nB * a.lam2;
+        const float nBl = nB * a.lam2, thr1 = rv.y;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const float4 t1 = tab[c];
@@ -330,105 +361,96 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         }
       }
       if (k > 0) mbar_wait(bar(P_STORED), (k - 1) & 1);     // the TMA store of tile k-1 has read the U1 buffer
-      st_shared_v4(sbase + L::U1 + seg0, prmt(ub[0], ub[1], 0x5410), prmt(ub[2], ub[3], 0x5410), prmt(ub[4], ub[5], 0x5410),
-                   prmt(ub[6], ub[7], 0x5410));
-      st_shared_v4(sbase + L::U1 + seg1, prmt(ub[8], ub[9], 0x5410), prmt(ub[10], ub[11], 0x5410),
-                   prmt(ub[12], ub[13], 0x5410), prmt(ub[14], ub[15], 0x5410));
-      st_shared_v4(sbase + L::U2 + seg0, prmt(ub[0], ub[1], 0x7632), prmt(ub[2], ub[3], 0x7632), prmt(ub[4], ub[5], 0x7632),
-                   prmt(ub[6], ub[7], 0x7632));
-      st_shared_v4(sbase + L::U2 + seg1, prmt(ub[8], ub[9], 0x7632), prmt(ub[10], ub[11], 0x7632),
-                   prmt(ub[12], ub[13], 0x7632), prmt(ub[14], ub[15], 0x7632));
+      {
+        const float dDA = -0.5f * c1A * kapA;
+#pragma unroll
+        for (int hseg = 0; hseg < 2; ++hseg) {
+          const uint32_t so = hseg ? seg1 : seg0;
+          uint32_t w1[4], w2[4], e1[4], e2[4];
+#pragma unroll
+          for (int p2 = 0; p2 < 4; ++p2) {
+            const int c = hseg * 8 + p2 * 2;
+            w1[p2] = prmt(ub[c], ub[c + 1], 0x5410);
+            w2[p2] = prmt(ub[c], ub[c + 1], 0x7632);
+            e1[p2] = pack_bf16(bf16_lo(ub[c]) * dDA, bf16_lo(ub[c + 1]) * dDA);
+            e2[p2] = pack_bf16(bf16_hi(ub[c]) * tab[32 + c].z, bf16_hi(ub[c + 1]) * tab[32 + c + 1].z);
+          }
+          st_shared_v4(sbase + L::U1 + so, w1[0], w1[1], w1[2], w1[3]);
+          st_shared_v4(sbase + L::U2 + so, w2[0], w2[1], w2[2], w2[3]);
+          st_shared_v4(sbase + L::UD1 + so, e1[0], e1[1], e1[2], e1[3]);
+          st_shared_v4(sbase + L::UD2 + so, e2[0], e2[1], e2[2], e2[3]);
+        }
+      }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(U_READY));
+      TRC(3);
 
-      // ---------------- phase 2: dA of both directions, UD = u dD, l2-norm backward sums ----------------
+      // ---------------- phase 2: dA of both directions, l2-norm backward sums ----------------
+      // (u is re-read from the operand tiles, Q = dA1 nA + dA2 nB + (c1A u1 + c1B u2) / leaky'(x) is parked in
+      //  this thread's own Y1 columns: nothing but x stays in registers across the phases)
       mbar_wait(bar(Y_DONE), ph);
       tc_fence_after();
-      float Q[16];                              // dA1 nA + dA2 nB
+      TRC(4);
       float tB = 0.f;
       float tA;
       {
-        // i2t direction.  Columns are visited as (c, c+1, c+8, c+9) so that the first butterfly step of the
-        // lanes->columns reduction of A1 dA1 can be folded in immediately (8 live partials instead of 16).
-        float y[16], p8[8];
-        uint32_t d1[8];
-        tmem_ld16(tmem + cY1 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
-        tmem_ld_wait();
-        const bool up8 = (lane & 8) != 0;
+        float p8[8];
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          float a1[4], pa[4];
+        for (int half = 0; half < 2; ++half) {
+          float y1[8], y2[8], Qh[8];
+          uint32_t ua[4], ubb[4];
+          const uint32_t so = half ? seg1 : seg0;
+          tmem_ld8(tmem + cY1 + lane_off + g * 16 + half * 8, reinterpret_cast<uint32_t*>(y1));
+          tmem_ld8(tmem + cY2 + lane_off + g * 16 + half * 8, reinterpret_cast<uint32_t*>(y2));
+          ld_shared_v4(sbase + L::U1 + so, ua[0], ua[1], ua[2], ua[3]);
+          ld_shared_v4(sbase + L::U2 + so, ubb[0], ubb[1], ubb[2], ubb[3]);
+          tmem_ld_wait();
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int cc = c + (h & 1) + (h >> 1) * 8;
-            const float4 t2 = tab[16 + cc];     // lambda c1B, kapB, dDB, nA
-            const float xv = x[cc];
-            const float uA = bf16_lo(ub[cc]);
-            const float dAA = lc1A * uA * fmaf(-kapA, y[cc], xv);
-            const float E = dAA * t2.w;
-            Q[cc] = E;
-            pa[h] = leaky(xv) * E;
-            a1[h] = uA * dDA;
+          for (int c2 = 0; c2 < 8; c2 += 2) {
+            float pa[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int cc = half * 8 + c2 + h;
+              const float4 t2 = tab[16 + cc];   // lambda c1B, kapB, nA, c1B
+              const float xv = x[cc], l = leaky(xv);
+              const float uA = h ? bf16_hi(ua[c2 >> 1]) : bf16_lo(ua[c2 >> 1]);
+              const float uB = h ? bf16_hi(ubb[c2 >> 1]) : bf16_lo(ubb[c2 >> 1]);
+              const float dAA = lc1A * uA * fmaf(-kapA, y1[c2 + h], xv);
+              const float dAB = t2.x * uB * fmaf(-t2.y, y2[c2 + h], xv);
+              const float E = dAA * t2.z, F = dAB * nB;
+              const float hh = fmaf(c1A, uA, t2.w * uB);
+              pa[h] = l * E;
+              tB = fmaf(l, F, tB);
+              Qh[c2 + h] = (E + F) + (xv > 0.f ? hh : 10.f * hh);
+            }
+            // first butterfly step (lane bit 0 <-> column bit 0) of the lanes->columns reduction of A1 dA1
+            const bool up1 = (lane & 1) != 0;
+            const float send = up1 ? pa[0] : pa[1], keep = up1 ? pa[1] : pa[0];
+            p8[(half * 8 + c2) >> 1] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
           }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float send = up8 ? pa[h] : pa[h + 2];
-            const float keep = up8 ? pa[h + 2] : pa[h];
-            p8[c + h] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-          }
-          d1[c >> 1] = pack_bf16(a1[0], a1[1]);
-          d1[(c >> 1) + 4] = pack_bf16(a1[2], a1[3]);
+          tmem_st8(tmem + cY1 + lane_off + g * 16 + half * 8, reinterpret_cast<const uint32_t*>(Qh));
         }
-        st_shared_v4(sbase + L::UD1 + seg0, d1[0], d1[1], d1[2], d1[3]);
-        st_shared_v4(sbase + L::UD1 + seg1, d1[4], d1[5], d1[6], d1[7]);
-        // t_A[text, region] = sum over the 32 words of this text of A1 dA1: lane l ends with column l & 15
+        // remaining steps: p8[e] holds column 2e + (lane & 1); lane bit h <-> column bit h
 #pragma unroll
         for (int h = 4; h >= 1; h >>= 1) {
-          const bool up = (lane & h) != 0;
+          const bool up = (lane & (2 * h)) != 0;
 #pragma unroll
           for (int e = 0; e < h; ++e) {
             const float send = up ? p8[e] : p8[e + h];
             const float keep = up ? p8[e + h] : p8[e];
-            p8[e] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            p8[e] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * h);
           }
         }
-        tA = p8[0] + __shfl_xor_sync(0xffffffffu, p8[0], 16);
-      }
-      {
-        // t2i direction
-        float y[16];
-        uint32_t d2[8];
-        tmem_ld16(tmem + cY2 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; c += 2) {
-          float a2[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cc = c + h;
-            const float4 t2 = tab[16 + cc];
-            const float xv = x[cc];
-            const float uB = bf16_hi(ub[cc]);
-            const float dAB = t2.x * uB * fmaf(-t2.y, y[cc], xv);
-            const float F = dAB * nB;
-            tB = fmaf(leaky(xv), F, tB);
-            Q[cc] += F;
-            a2[h] = uB * t2.z;
-          }
-          d2[c >> 1] = pack_bf16(a2[0], a2[1]);
-        }
-        st_shared_v4(sbase + L::UD2 + seg0, d2[0], d2[1], d2[2], d2[3]);
-        st_shared_v4(sbase + L::UD2 + seg1, d2[4], d2[5], d2[6], d2[7]);
+        tA = p8[0] + __shfl_xor_sync(0xffffffffu, p8[0], 16);   // lane l: column l & 15, summed over 32 words
       }
       tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(UD_READY));
       s_tbp[g * kRows + m] = tB;
       if (lane < 16) reinterpret_cast<float*>(tab + 32 + cl)[0] = nA_cl * nA_cl * tA;
+      TRC(5);
       named_bar_sync(1 + q, 32 * NC);           // the NC warps that share this text slot
+      TRC(6);
       float zB = 0.f;
 #pragma unroll
       for (int gg = 0; gg < NC; ++gg) zB += s_tbp[gg * kRows + m];
@@ -436,39 +458,54 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
 
       // ------------------------------ phase 3: dS, P ------------------------------
       uint32_t pk[8];
+      tmem_st_wait();
 #pragma unroll
-      for (int c = 0; c < 16; c += 2) {
-        float pv[2];
+      for (int half = 0; half < 2; ++half) {
+        float Qh[8];
+        tmem_ld8(tmem + cY1 + lane_off + g * 16 + half * 8, reinterpret_cast<uint32_t*>(Qh));
+        tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cc = c + h;
-          const float4 t3 = tab[32 + cc];       // nA^2 tA, c1B, alpha
-          const float xv = x[cc], l = leaky(xv);
-          const float uA = bf16_lo(ub[cc]), uB = bf16_hi(ub[cc]);
-          const float dS = leaky_grad(xv) * fmaf(-l, t3.x + zB, Q[cc]) + fmaf(c1A, uA, t3.y * uB);
-          pv[h] = dS * (t3.z * beta_m);
+        for (int c2 = 0; c2 < 8; c2 += 2) {
+          float pv[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = half * 8 + c2 + h;
+            const float4 t3 = tab[32 + cc];     // nA^2 tA, alpha
+            const float xv = x[cc];
+            const float dS = leaky_grad(xv) * fmaf(-leaky(xv), t3.x + zB, Qh[c2 + h]);
+            pv[h] = dS * (t3.y * beta_m);
+          }
+          pk[(half * 8 + c2) >> 1] = pack_bf16(pv[0], pv[1]);
         }
-        pk[c >> 1] = pack_bf16(pv[0], pv[1]);
       }
+      TRC(7);
       mbar_wait(bar(DG_DONE), ph);              // the dG GEMMs have consumed U1 / U2: U1 takes P
+      TRC(8);
       st_shared_v4(sbase + L::U1 + seg0, pk[0], pk[1], pk[2], pk[3]);
       st_shared_v4(sbase + L::U1 + seg1, pk[4], pk[5], pk[6], pk[7]);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(P_READY));
+      TRC(9);
 
       // ------------------------------ Gram gradients leave TMEM ------------------------------
       tc_fence_after();
       if (g < 2) {
-        // dG^T block of this text (rows = this word), 16 of its 32 columns per warpgroup
+        // dG^T block of this text (rows = this word), 16 of its 32 columns per warpgroup: staged in shared memory
+        // (row-major, exactly the global layout) and added to global memory by ONE bulk reduce of the store warp
         float v[16];
         tmem_ld16(tmem + cDGT + lane_off + q * 32 + g * 16, reinterpret_cast<uint32_t*>(v));
         tmem_ld_wait();
-        if (j < a.Bt) {
-          float* dst = a.dgt + ((size_t)jt * kRows + m) * kW + g * 16;
+        // 16-byte chunks of a row are XOR-swizzled with the row index (conflict-free stores); the global dG^T
+        // buffer keeps the same permutation and epilogue.cu undoes it (dgt_swz)
+        const uint32_t dst = sbase + L::GBD + (uint32_t)m * (kW * 4);
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) red_add_v4(dst + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
-        }
+        for (int c = 0; c < 4; ++c)
+          st_shared_v4(dst + (((uint32_t)(g * 4 + c) ^ (uint32_t)(lane & 7)) << 4), __float_as_uint(v[4 * c]),
+                       __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(DGT_STAGED));
       }
       if (last_of_video && q * 32 < R) {
         // dG^V rows (TMEM lanes = regions), this warpgroup's 16 columns
@@ -482,6 +519,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         }
       }
       tc_fence_before();
+      TRC(10);
       if (++jt == tpv) { jt = 0; ++i; }
     }
   }
@@ -544,6 +582,7 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, float lambda, 
   a.rowv = (const float4*)(ws + Lw.rowv); a.colv = (const float4*)(ws + Lw.colv);
   a.lam = lambda; a.lam2 = lambda * kLog2e;
   a.dgv = (float*)(ws + Lw.dgv); a.dgt = (float*)(ws + Lw.dgt);
+  a.trace = (long long*)g_trace_buffer;
   int dev = 0, sms = 148;
   DVLP_CUDA_OK(cudaGetDevice(&dev));
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -9,9 +9,15 @@ import torch
 from demovlp_b200 import _lib, ops, synth
 
 ROLES = ["tma", "mma", "grpA(w4)", "grpB(w8)", "grpB(w12)"]
-EV_MMA = ["S issue", "S committed", "U ready", "Y committed", "UD ready", "dG committed", "P ready", "grad committed"]
-EV_GRP = ["start", "S done", "pass1 done", "norm bar", "U written", "Y done", "UD written", "t sums", "dG done",
-          "P written", "grad done", "flushed"]
+if os.environ.get("DVLP_TC_BWD", "2") == "1":
+    EV_MMA = ["S issue", "S committed", "U ready", "Y committed", "UD ready", "dG committed", "P ready", "grad committed"]
+    EV_GRP = ["start", "S done", "pass1 done", "norm bar", "U written", "Y done", "UD written", "t sums", "dG done",
+              "P written", "grad done", "flushed"]
+else:   # pair_bwd2.cu
+    ROLES = ["tma", "mma", "cw(g0,q0)", "cw(last)", "-"]
+    EV_MMA = ["U ready", "Y issued", "UD ready", "dG issued", "next S issued"]
+    EV_GRP = ["start", "vec full", "S done", "U arrive", "Y done", "UD arrive", "tB bar", "P computed", "dG done",
+              "P arrive", "flushed"]
 
 
 def main():
