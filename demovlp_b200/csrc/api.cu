@@ -61,6 +61,9 @@ int run_pair_bwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R
 int run_grad_gemm2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
                    const Workspace& L, cudaStream_t st);
 int tc_bwd_version();
+int run_pair_fwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
+                  float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
+int tc_fwd_version();
 extern void* g_trace_buffer;
 
 Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc) {
@@ -220,6 +223,7 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
   if (tc) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
+    if (tc_fwd_version() == 2) return run_pair_fwd2(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, true, st);
     return run_pair_tc_fwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, st);
   }
   PairArgs a{};

@@ -784,6 +784,16 @@ int tc_bwd_version() {
   return v;
 }
 
+// DVLP_TC_FWD=1: first tcgen05 forward (pair_tc.cu); default 2: pair_fwd2.cu
+int tc_fwd_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVLP_TC_FWD");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 int run_pair_tc_bwd(const void* vb, const void* tb, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
                     const float* d_scores, char* ws, const Workspace& L, cudaStream_t st) {
   if (d != tcb::kD || W != tcb::kW) return DVLP_ERR_BAD_SHAPE;
