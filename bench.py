@@ -231,13 +231,44 @@ def run_ours(args):
         step(resident)
     sync()
 
+    # ---- whole-step CUDA graphs (demovlp_b200.graph): forward + backward + loss stacking in one launch.
+    #      Two instances so that the end-to-end loop can fill one set of static inputs while the other computes.
+    gsteps = None
+    if not args.no_graph:
+        try:
+            from demovlp_b200.graph import GraphedLossStep
+
+            def fn(t):
+                first = (t["g_text"], t["g_vid"]) if world > 1 else L.sim_matrix(t["g_text"], t["g_vid"])
+                return mod(first, t["im"], t["s"], t["im_mask"], s_len, t["s_mask"])
+
+            gsteps = [GraphedLossStep(fn, resident, ("im", "s", "g_text", "g_vid"), warmup=2) for _ in range(2)]
+        except Exception as e:      # capture not possible (e.g. a collective that cannot be captured): eager steps
+            if rank == 0:
+                print(f"bench: CUDA graph capture failed ({type(e).__name__}: {e}); timing eager steps", file=sys.stderr)
+            gsteps = None
+        if world > 1:               # all ranks must take the same path
+            ok = torch.tensor([1 if gsteps else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if not int(ok.item()):
+                gsteps = None
+    sync()
+
+    def run_step():
+        if gsteps:
+            gsteps[0].replay()
+        else:
+            step(resident)
+
+    for _ in range(max(3, args.warmup)):
+        run_step()
+    sync()
+
     # ---- timed region: K steps, device time per step via CUDA events, L2 flushed between steps
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    _lib.profile_enable(True)
-    _lib.profile_read()
     evs = []
     sync()
     wall0 = time.perf_counter()
@@ -245,15 +276,13 @@ def run_ours(args):
         flush.zero_()
         a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        step(resident)
+        run_step()
         c.record()
         evs.append((a, c))
     sync()
     wall = time.perf_counter() - wall0
     sampler.stop_flag = True
-    _lib.profile_enable(False)
-    prof = _lib.profile_read()
-    launches = _lib.launch_count() - launches0
+    launches = (gsteps[0].launches_per_replay * args.steps) if gsteps else (_lib.launch_count() - launches0)
     dev_ms = sum(a.elapsed_time(c) for a, c in evs)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -262,17 +291,54 @@ def run_ours(args):
     pairs_step = B * B
     value = pairs_step * args.steps / (dev_ms * 1e-3)
 
-    # ---- end to end: pinned host inputs -> H2D -> public API -> D2H of the loss triple, every step
+    # ---- per-kernel device times (CUDA events recorded by the library around its kernels; eager steps)
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    for _ in range(10):
+        flush.zero_()
+        step(resident)
+    sync()
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+
+    # ---- end to end: pinned host inputs -> H2D -> public API -> D2H of the loss triple, every step.
+    #      The copy of step k+1's inputs runs on a copy stream under step k's kernels (two sets of buffers);
+    #      the host waits for every step's loss triple before it enqueues the next step.
     sync()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     out_host = torch.empty(3, dtype=torch.float32).pin_memory()
     e_steps = args.steps
+    main = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
+    bufs = [gs.inputs for gs in gsteps] if gsteps else [{k: v.clone() for k, v in resident.items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[slot])          # the previous user of this buffer set has finished
+            with torch.no_grad():
+                for k, v in host.items():
+                    bufs[slot][k].copy_(v, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    done[0].record(main); done[1].record(main)
+    sync()
     e0.record()
-    for _ in range(e_steps):
-        t_dev = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        loss, gl, ll = step(t_dev)
-        out_host.copy_(torch.stack([loss.detach(), gl.detach(), ll.detach()]), non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the loss every step (.item() in the trainer)
+    upload(0)
+    for it in range(e_steps):
+        slot = it & 1
+        main.wait_event(ready[slot])
+        if gsteps:
+            losses = gsteps[slot].replay()
+        else:
+            loss, gl, ll = step(bufs[slot])
+            losses = torch.stack([loss.detach(), gl.detach(), ll.detach()])
+        out_host.copy_(losses, non_blocking=True)
+        done[slot].record(main)
+        if it + 1 < e_steps:
+            upload(slot ^ 1)
+        main.synchronize()                              # the caller reads the loss every step (.item() in the trainer)
     e1.record()
     sync()
     e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -309,7 +375,9 @@ def run_ours(args):
                        "parallelism": f"video-row sharding x{world}" if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
                        "kernel_path": "tcgen05" if tc else "generic fp32 CUDA cores",
-                       "wall_ms_per_step_incl_flush": wall / args.steps * 1e3},
+                       "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
+                       "cuda_graph": bool(gsteps),
+                       "e2e_pipeline": "H2D of step k+1 on a copy stream under step k; host waits for each step's loss"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
@@ -330,6 +398,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of whole-step CUDA graph replays")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
