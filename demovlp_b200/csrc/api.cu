@@ -39,11 +39,11 @@ int run_pair_generic(bool backward, const PairArgs& a, int n_cta, cudaStream_t s
 int run_grad_finalize(const void*, int, const float*, const float*, const float*, int, int, int, int, float*,
                       cudaStream_t);
 int run_grad_finalize_tc(const void*, const void*, const float*, const float*, const float*, const float*, const float*,
-                         const float*, int, int, int, int, int, float*, float*, cudaStream_t);
+                         const float*, int, int, int, int, int, void*, void*, int, cudaStream_t);
 int run_rwa_loss(const float*, int, int, int, int, float, float*, float*, cudaStream_t);
 int run_normsoftmax(const float*, int, int, float, float*, float*, float*, cudaStream_t);
 int run_sim_fwd(const void*, const void*, int, int, int, float, int, float*, float*, cudaStream_t);
-int run_sim_bwd(const void*, const void*, int, int, int, float, int, const float*, float*, float*, float*,
+int run_sim_bwd(const void*, const void*, int, int, int, float, int, const float*, void*, void*, int, float*,
                 cudaStream_t);
 int run_ranks_t2v(const double*, int, int, int32_t*, cudaStream_t);
 int run_ranks_v2t(const double*, int, int, double*, cudaStream_t);
@@ -238,11 +238,12 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
 
 int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
                        int R, int W, int d, float lambda, int focal_equal, int in_dtype, int impl,
-                       const float* d_scores, float* d_im, float* d_s, void* workspace, size_t workspace_bytes,
-                       void* stream) {
+                       const float* d_scores, void* d_im, void* d_s, int out_dtype, void* workspace,
+                       size_t workspace_bytes, void* stream) {
   int rc = check_common(im, s, im_mask, s_mask, Bv, Bt, R, W, d, in_dtype);
   if (rc) return rc;
   if (!d_scores || !d_im || !d_s) return DVLP_ERR_NULL_POINTER;
+  if (out_dtype != DVLP_F32 && out_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
   bool tc = false;
   if ((rc = pick_tc(impl, R, W, d, &tc))) return rc;
   if ((rc = device_ok())) return rc;
@@ -287,12 +288,13 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   if (prescaled && d == 256 && (R % 16) == 0 && (W % 16) == 0 && R <= 128 && W <= 128)
     return run_grad_finalize_tc(xv, xt, (const float*)(ws + L.alpha), (const float*)(ws + L.beta),
                                 (const float*)(ws + L.dvh), (const float*)(ws + L.dth), (const float*)(ws + L.dgv),
-                                (const float*)(ws + L.dgt), Bv, Bt, R, W, dgt_swz, d_im, d_s, st);
+                                (const float*)(ws + L.dgt), Bv, Bt, R, W, dgt_swz, d_im, d_s, out_dtype, st);
+  if (out_dtype != DVLP_F32) return DVLP_ERR_BAD_DTYPE;       // the fp32 CUDA-core finalisation writes fp32 only
   if ((rc = run_grad_finalize(xv, xdt, (const float*)(ws + L.alpha), (const float*)(ws + L.dvh),
-                              (const float*)(ws + L.dgv), Bv, R, d, prescaled, d_im, st)))
+                              (const float*)(ws + L.dgv), Bv, R, d, prescaled, (float*)d_im, st)))
     return rc;
   return run_grad_finalize(xt, xdt, (const float*)(ws + L.beta), (const float*)(ws + L.dth),
-                           (const float*)(ws + L.dgt), Bt, W, d, prescaled, d_s, st);
+                           (const float*)(ws + L.dgt), Bt, W, d, prescaled, (float*)d_s, st);
 }
 
 int dvlp_rwa_loss_fwd_bwd(const float* scores, int n_rows, int n_cols, int row_offset, int n_total, float lambda,
@@ -316,13 +318,14 @@ int dvlp_sim_matrix_fwd(const void* a, const void* b, int N, int M, int d, float
 }
 
 int dvlp_sim_matrix_bwd(const void* a, const void* b, int N, int M, int d, float eps, int in_dtype,
-                        const float* d_out, float* d_a, float* d_b, float* scratch, void* stream) {
+                        const float* d_out, void* d_a, void* d_b, int out_dtype, float* scratch, void* stream) {
   if (!a || !b || !d_out || !scratch) return DVLP_ERR_NULL_POINTER;
   if (N <= 0 || M <= 0 || d <= 0) return DVLP_ERR_BAD_SHAPE;
   if (in_dtype != DVLP_F32 && in_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
+  if (out_dtype != DVLP_F32 && out_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
   int rc = device_ok();
   if (rc) return rc;
-  return run_sim_bwd(a, b, N, M, d, eps, in_dtype, d_out, d_a, d_b, scratch, (cudaStream_t)stream);
+  return run_sim_bwd(a, b, N, M, d, eps, in_dtype, d_out, d_a, d_b, out_dtype, scratch, (cudaStream_t)stream);
 }
 
 int dvlp_normsoftmax_fwd_bwd(const float* x, int N, int M, float temperature, float* loss, float* d_x,

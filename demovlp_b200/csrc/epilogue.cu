@@ -126,12 +126,13 @@ __global__ void __launch_bounds__(256) k_grad_finalize_tile(const Tin* __restric
 //   d_x_r = D_r - inv_r^2 (x_r . D_r) x_r                       (the l2norm backward, model/loss.py:333-338)
 // Warp w owns rows 16w..16w+15 and all 256 columns (128 accumulator registers per thread).
 constexpr int kFinLdX = (256 + 8) * 2;      // bytes
+template <bool OUT_BF16>
 __global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ t,
                                                        const float* __restrict__ alpha, const float* __restrict__ beta,
                                                        const float* __restrict__ dvh, const float* __restrict__ dth,
                                                        const float* __restrict__ dgv, const float* __restrict__ dgt,
-                                                       int Bv, int R, int W, int dgt_swz, float* __restrict__ d_im,
-                                                       float* __restrict__ d_s) {
+                                                       int Bv, int R, int W, int dgt_swz, void* __restrict__ d_im,
+                                                       void* __restrict__ d_s) {
   extern __shared__ __align__(16) uint8_t fsm[];
   __shared__ float s_inv[128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __re
   const float* inv = (text ? beta : alpha) + (size_t)item * L;
   const float* dX = (text ? dth : dvh) + (size_t)item * L * 256;
   const float* dG = (text ? dgt : dgv) + (size_t)item * L * L;
-  float* out = (text ? d_s : d_im) + (size_t)item * L * 256;
+  void* out_base = text ? d_s : d_im;
+  const size_t out_off = (size_t)item * L * 256;
   const int ldA = (L + 8) * 2;
   uint8_t* xs = fsm;                         // [L][264] bf16 raw rows
   uint8_t* as = fsm + (size_t)L * kFinLdX;   // [L][L+8] bf16: 2 inv_r inv_c dG[r][c]
@@ -207,25 +209,38 @@ __global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __re
     o_lo.y = fmaf(-k_lo, __uint_as_float(x_lo & 0xffff0000u), acc[n][1]);
     o_hi.x = fmaf(-k_hi, __uint_as_float(x_hi << 16), acc[n][2]);
     o_hi.y = fmaf(-k_hi, __uint_as_float(x_hi & 0xffff0000u), acc[n][3]);
-    *reinterpret_cast<float2*>(out + (size_t)r_lo * 256 + c) = o_lo;
-    *reinterpret_cast<float2*>(out + (size_t)r_hi * 256 + c) = o_hi;
+    if (OUT_BF16) {
+      __nv_bfloat16* ob = (__nv_bfloat16*)out_base + out_off;
+      *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)r_lo * 256 + c) = __floats2bfloat162_rn(o_lo.x, o_lo.y);
+      *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)r_hi * 256 + c) = __floats2bfloat162_rn(o_hi.x, o_hi.y);
+    } else {
+      float* of = (float*)out_base + out_off;
+      *reinterpret_cast<float2*>(of + (size_t)r_lo * 256 + c) = o_lo;
+      *reinterpret_cast<float2*>(of + (size_t)r_hi * 256 + c) = o_hi;
+    }
   }
 }
 
 // both sides in one launch (tcgen05 path)
 int run_grad_finalize_tc(const void* v, const void* t, const float* alpha, const float* beta, const float* dvh,
                          const float* dth, const float* dgv, const float* dgt, int Bv, int Bt, int R, int W, int dgt_swz,
-                         float* d_im, float* d_s, cudaStream_t st) {
+                         void* d_im, void* d_s, int out_dtype, cudaStream_t st) {
   const int Lmax = R > W ? R : W;
   const size_t smem = (size_t)Lmax * kFinLdX + (size_t)Lmax * (Lmax + 8) * 2;
   static bool attr_set = false;
   if (!attr_set) {
-    DVLP_CUDA_OK(cudaFuncSetAttribute(k_finalize_item, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_finalize_item<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      128 * kFinLdX + 128 * 136 * 2));
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_finalize_item<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       128 * kFinLdX + 128 * 136 * 2));
     attr_set = true;
   }
-  k_finalize_item<<<Bv + Bt, 256, smem, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)t, alpha, beta, dvh, dth,
-                                              dgv, dgt, Bv, R, W, dgt_swz, d_im, d_s);
+  if (out_dtype == DVLP_BF16)
+    k_finalize_item<true><<<Bv + Bt, 256, smem, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)t, alpha, beta, dvh,
+                                                      dth, dgv, dgt, Bv, R, W, dgt_swz, d_im, d_s);
+  else
+    k_finalize_item<false><<<Bv + Bt, 256, smem, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)t, alpha, beta, dvh,
+                                                       dth, dgv, dgt, Bv, R, W, dgt_swz, d_im, d_s);
   DVLP_LAUNCH_OK();
   return DVLP_OK;
 }

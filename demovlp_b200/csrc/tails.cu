@@ -339,17 +339,25 @@ static int sim_bwd_t(const T* a, const T* b, int N, int M, int d, float eps, con
   return DVLP_OK;
 }
 
+int run_sim_fwd_mma(const void* a, const void* b, int N, int M, float eps, float* out, cudaStream_t st);
+int run_sim_bwd_mma(const void* a, const void* b, int N, int M, float eps, const float* d_out, void* d_a, void* d_b,
+                    int out_dtype, float* scratch, cudaStream_t st);
+
 int run_sim_fwd(const void* a, const void* b, int N, int M, int d, float eps, int dt, float* out, float* scratch,
                 cudaStream_t st) {
+  if (dt == DVLP_BF16 && d == 256) return run_sim_fwd_mma(a, b, N, M, eps, out, st);
   if (dt == DVLP_BF16)
     return sim_fwd_t((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, N, M, d, eps, out, scratch, st);
   return sim_fwd_t((const float*)a, (const float*)b, N, M, d, eps, out, scratch, st);
 }
-int run_sim_bwd(const void* a, const void* b, int N, int M, int d, float eps, int dt, const float* d_out, float* d_a,
-                float* d_b, float* scratch, cudaStream_t st) {
+int run_sim_bwd(const void* a, const void* b, int N, int M, int d, float eps, int dt, const float* d_out, void* d_a,
+                void* d_b, int out_dtype, float* scratch, cudaStream_t st) {
+  if (dt == DVLP_BF16 && d == 256) return run_sim_bwd_mma(a, b, N, M, eps, d_out, d_a, d_b, out_dtype, scratch, st);
+  if (out_dtype != DVLP_F32) return DVLP_ERR_BAD_DTYPE;      // the fp32 CUDA-core kernels write fp32 only
   if (dt == DVLP_BF16)
-    return sim_bwd_t((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, N, M, d, eps, d_out, d_a, d_b, scratch, st);
-  return sim_bwd_t((const float*)a, (const float*)b, N, M, d, eps, d_out, d_a, d_b, scratch, st);
+    return sim_bwd_t((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, N, M, d, eps, d_out, (float*)d_a, (float*)d_b,
+                     scratch, st);
+  return sim_bwd_t((const float*)a, (const float*)b, N, M, d, eps, d_out, (float*)d_a, (float*)d_b, scratch, st);
 }
 
 int run_ranks_t2v(const double* sims, int Nq, int Nv, int32_t* ranks, cudaStream_t st) {

@@ -2,6 +2,8 @@
 the arithmetic is all in libdemovlp_b200.so)."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -46,19 +48,24 @@ def rw_scores_fwd_raw(im, s, im_mask, s_mask, lam, focal_equal, impl):
     return scores, (im, s, im_mask, s_mask, ws, float(lam), int(focal_equal), dt, impl)
 
 
-def rw_scores_bwd_raw(state, d_scores):
-    """Plain backward: fp32 (d_im, d_s) for the state returned by rw_scores_fwd_raw."""
+def rw_scores_bwd_raw(state, d_scores, out_dtype=torch.float32):
+    """Plain backward: (d_im, d_s) for the state returned by rw_scores_fwd_raw, fp32 unless ``out_dtype`` is
+    bf16 and the tcgen05 path serves the shape (its finalisation kernel then writes bf16 directly)."""
     im, s, im_mask, s_mask, ws, lam, focal_equal, dt, impl = state
     lib = _lib.load()
     Bv, R, d = im.shape
     Bt, W, _ = s.shape
     d_scores = d_scores.to(torch.float32).contiguous()
-    d_im = torch.empty(Bv, R, d, dtype=torch.float32, device=im.device)
-    d_s = torch.empty(Bt, W, d, dtype=torch.float32, device=im.device)
+    direct = (out_dtype == torch.bfloat16 and impl != _lib.IMPL_GENERIC and lib.dvlp_rw_tcgen05_supported(R, W, d)
+              and os.environ.get("DVLP_TC_BWD", "2") != "0")
+    odt = torch.bfloat16 if direct else torch.float32
+    d_im = torch.empty(Bv, R, d, dtype=odt, device=im.device)
+    d_s = torch.empty(Bt, W, d, dtype=odt, device=im.device)
     with torch.cuda.device(im.device):
         rc = lib.dvlp_rw_scores_bwd(_lib.ptr(im), _lib.ptr(s), _lib.ptr(im_mask), _lib.ptr(s_mask),
                                     Bv, Bt, R, W, d, lam, focal_equal, dt, impl,
                                     _lib.ptr(d_scores), _lib.ptr(d_im), _lib.ptr(d_s),
+                                    _lib.BF16 if direct else _lib.F32,
                                     _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
     _lib.check(rc, "rw_scores_bwd")
     return d_im, d_s
@@ -77,7 +84,7 @@ class _RWScores(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_scores):
         state = tuple(ctx.saved_tensors) + tuple(ctx.cfg)
-        d_im, d_s = rw_scores_bwd_raw(state, d_scores)
+        d_im, d_s = rw_scores_bwd_raw(state, d_scores, out_dtype=state[0].dtype)
         return d_im.to(state[0].dtype), d_s.to(state[1].dtype), None, None, None, None, None
 
 
@@ -188,12 +195,15 @@ class _SimMatrix(torch.autograd.Function):
         N, d = a.shape
         M = b.shape[0]
         d_out = d_out.to(torch.float32).contiguous()
-        d_a = torch.empty(N, d, dtype=torch.float32, device=a.device) if ctx.needs_input_grad[0] else None
-        d_b = torch.empty(M, d, dtype=torch.float32, device=a.device) if ctx.needs_input_grad[1] else None
+        # bf16 embeddings of width 256 take the mma.sync kernels, which write the gradients in bf16 directly
+        odt = a.dtype if (a.dtype == torch.bfloat16 and d == 256) else torch.float32
+        d_a = torch.empty(N, d, dtype=odt, device=a.device) if ctx.needs_input_grad[0] else None
+        d_b = torch.empty(M, d, dtype=odt, device=a.device) if ctx.needs_input_grad[1] else None
         scratch = torch.empty(N + M, dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
             rc = lib.dvlp_sim_matrix_bwd(_lib.ptr(a), _lib.ptr(b), N, M, d, ctx.eps, _lib.dtype_code(a),
-                                         _lib.ptr(d_out), _lib.ptr(d_a), _lib.ptr(d_b), _lib.ptr(scratch),
+                                         _lib.ptr(d_out), _lib.ptr(d_a), _lib.ptr(d_b),
+                                         _lib.BF16 if odt == torch.bfloat16 else _lib.F32, _lib.ptr(scratch),
                                          _lib.stream_ptr())
         _lib.check(rc, "sim_matrix_bwd")
         return (d_a.to(a.dtype) if d_a is not None else None,

@@ -87,13 +87,14 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
 
 /*
  * Backward of dvlp_rw_scores_fwd (what autograd does through model/loss.py:209-330):
- * given d_scores (Bv, Bt) fp32 produces d_im (Bv, R, d) fp32 and d_s (Bt, W, d) fp32
- * (both overwritten).  The attention tensors are recomputed, never stored.
+ * given d_scores (Bv, Bt) fp32 produces d_im (Bv, R, d) and d_s (Bt, W, d) in `out_dtype`
+ * (both overwritten; DVLP_F32 always, DVLP_BF16 on the tcgen05 path, else DVLP_ERR_BAD_DTYPE).
+ * The attention tensors are recomputed, never stored.
  * `workspace` must be the one the forward call used (same shape, inputs unchanged).
  */
 int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, const float* s_mask,
                        int Bv, int Bt, int R, int W, int d, float lambda, int focal_equal,
-                       int in_dtype, int impl, const float* d_scores, float* d_im, float* d_s,
+                       int in_dtype, int impl, const float* d_scores, void* d_im, void* d_s, int out_dtype,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
@@ -109,13 +110,14 @@ int dvlp_rwa_loss_fwd_bwd(const float* scores, int n_rows, int n_cols, int row_o
 
 /*
  * sim_matrix (model/model.py:582-590): out[i][j] = a_i . b_j / (max(|a_i|,eps) max(|b_j|,eps)).
- * a (N, d), b (M, d) fp32 or bf16, out (N, M) fp32.  Backward: given d_out produces d_a, d_b fp32
- * (either may be NULL).  `scratch` holds N + M floats (inverse norms).
+ * a (N, d), b (M, d) fp32 or bf16, out (N, M) fp32.  Backward: given d_out produces d_a, d_b
+ * (either may be NULL) in `out_dtype` (DVLP_F32 always; DVLP_BF16 for bf16 inputs with d == 256, else
+ * DVLP_ERR_BAD_DTYPE).  `scratch` holds N + M floats (inverse norms).
  */
 int dvlp_sim_matrix_fwd(const void* a, const void* b, int N, int M, int d, float eps, int in_dtype,
                         float* out, float* scratch, void* stream);
 int dvlp_sim_matrix_bwd(const void* a, const void* b, int N, int M, int d, float eps, int in_dtype,
-                        const float* d_out, float* d_a, float* d_b, float* scratch, void* stream);
+                        const float* d_out, void* d_a, void* d_b, int out_dtype, float* scratch, void* stream);
 
 /*
  * NormSoftmaxLoss (model/loss.py:126-138) on x (N, M) fp32:
