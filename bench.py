@@ -350,19 +350,35 @@ def run_ours(args):
         pk = peaks()
         pairs_rank = b_loc * B
         rwd = R * W * D
+        # algorithmic FLOPs per pair: forward 6 RWd; backward 12 RWd = 8 RWd in the pair kernel (the four
+        # attention-side contractions) + 4 RWd in the gradient GEMMs (dS -> dV, dS -> dT)
         kern = {}
-        for name, flops_per_pair in (("fwd", 6 * rwd), ("bwd", 12 * rwd)):
-            ms, n = prof[name]
+        for name, slot, flops_per_pair in (("fwd", "fwd", 6 * rwd), ("bwd_pair", "bwd", 8 * rwd), ("grad_gemm", "grad_gemm", 4 * rwd)):
+            ms, n = prof[slot]
             if n:
                 kern[name] = {"ms_per_launch": ms / n, "tflops": flops_per_pair * pairs_rank / (ms / n * 1e-3) / 1e12}
-        dom = max(kern, key=lambda k: kern[k]["ms_per_launch"]) if kern else None
+        for slot in ("prep", "final"):
+            ms, n = prof[slot]
+            if n:
+                kern[slot] = {"ms_per_launch": ms / n}
+        cand = [k for k in ("fwd", "bwd_pair") if k in kern]
+        dom = max(cand, key=lambda k: kern[k]["ms_per_launch"]) if cand else None
         roof = None
         if dom:
             a = kern[dom]["tflops"]
+            traffic = None
+            try:        # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same shape)
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                if world == 1:
+                    traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+            except Exception:
+                pass
             roof = {"bound": "tensor", "achieved": a, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": a / pk["bf16"],
-                    "traffic": None, "kernel": f"rw pair {dom} kernel",
-                    "algorithmic_flops_per_pair": (12 if dom == "bwd" else 6) * rwd,
-                    "pairs_per_launch": pairs_rank, "peak_source": pk["source"] + ", burst bf16",
+                    "traffic": traffic, "kernel": {"fwd": "k_pair_fwd2 (forward pair kernel)",
+                                                   "bwd_pair": "k_pair_bwd2 (backward pair kernel)"}[dom],
+                    "algorithmic_flops_per_pair": (8 if dom == "bwd_pair" else 6) * rwd,
+                    "pairs_per_launch": pairs_rank, "peak_source": pk["source"] + ", burst bf16 (SM clock stays at max)",
+                    "note": "co-bound by fp32 ALU/MUFU issue (softmax / focal / l2-norm work per element), see DESIGN.md",
                     "kernels": kern,
                     "step_algorithmic_tflops": 18 * rwd * pairs_step / world / (dev_ms / args.steps * 1e-3) / 1e12}
         tc = bool(lib.dvlp_rw_tcgen05_supported(R, W, D))

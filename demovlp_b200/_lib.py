@@ -108,9 +108,9 @@ def profile_enable(on: bool):
 
 
 def profile_read():
-    """{slot: (total_ms, count)} for fwd / bwd / prep / final since the last read."""
-    ms = (C.c_double * 4)()
-    cnt = (C.c_int * 4)()
+    """{slot: (total_ms, count)} for fwd / bwd / prep / final / grad_gemm since the last read."""
+    ms = (C.c_double * 5)()
+    cnt = (C.c_int * 5)()
     check(load().dvlp_profile_read(ms, cnt), "profile_read")
-    names = ("fwd", "bwd", "prep", "final")
+    names = ("fwd", "bwd", "prep", "final", "grad_gemm")
     return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}

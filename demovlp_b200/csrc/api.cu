@@ -47,24 +47,17 @@ int run_sim_bwd(const void*, const void*, int, int, int, float, int, const float
                 cudaStream_t);
 int run_ranks_t2v(const double*, int, int, int32_t*, cudaStream_t);
 int run_ranks_v2t(const double*, int, int, double*, cudaStream_t);
-// tcgen05 path (pair_tc.cu)
-bool tc_supported(int R, int W, int d);
-int run_pair_tc_fwd(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
-                    int focal, float* scores, char* ws, const Workspace& L, cudaStream_t st);
-int run_pair_tc_bwd(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
-                    int focal, const float* d_scores, char* ws, const Workspace& L, cudaStream_t st);
-bool tc_bwd_available();
-int run_grad_gemm(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
-                  const Workspace& L, cudaStream_t st);
+// tcgen05 path: pair_fwd2.cu, pair_bwd2.cu, grad_gemm2.cu
+int run_pair_fwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
+                  float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
 int run_pair_bwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
                   const float* d_scores, char* ws, const Workspace& L, cudaStream_t st);
 int run_grad_gemm2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
                    const Workspace& L, cudaStream_t st);
-int tc_bwd_version();
-int run_pair_fwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
-                  float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
-int tc_fwd_version();
-extern void* g_trace_buffer;
+void* g_trace_buffer = nullptr;   // set through dvlp_debug_set_trace (tools/trace_tiles.py)
+
+// shapes served by the tcgen05 kernels: d = 256, W = 32 words, R a multiple of 16 in [32, 80]
+bool tc_supported(int R, int W, int d) { return d == 256 && W == 32 && (R == 80 || R == 64 || R == 48 || R == 32); }
 
 Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc) {
   Workspace L{};
@@ -95,9 +88,6 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   {
     const size_t units = (size_t)Bv * ((Bt + 3) / 4);
     L.pa = take(tc ? units * R * 128 * 2 : 0);
-    L.pb = take(tc ? units * R * 128 * 2 : 0);
-    L.nrm_a = take(tc ? units * 4 * R * 4 : 0);
-    L.nrm_b = take(tc ? units * 128 * 4 : 0);
     L.rowv = take(tc ? units * 128 * 16 : 0);
     L.colv = take(tc ? units * 4 * R * 16 : 0);
     L.gbd = take(tc ? (size_t)((Bt + 3) / 4) * 128 * 128 * 2 : 0);
@@ -217,14 +207,13 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope p(kProfPrep, st);
-    if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, tc && !tc_bwd_available(), ws, L, st))) return rc;
+    if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, false, ws, L, st))) return rc;
   }
   ProfScope p(kProfFwd, st);
   if (tc) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
-    if (tc_fwd_version() == 2) return run_pair_fwd2(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, true, st);
-    return run_pair_tc_fwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, st);
+    return run_pair_fwd2(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, true, st);
   }
   PairArgs a{};
   a.vh = (const float*)(ws + L.vh); a.th = (const float*)(ws + L.th);
@@ -251,22 +240,22 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
-  // zero the accumulators (one contiguous range: dvh .. dgt)
-  DVLP_CUDA_OK(cudaMemsetAsync(ws + L.dvh, 0, L.pa - L.dvh, st));
+  // zero the accumulators (one contiguous range: dvh .. dgt; the tcgen05 dV' GEMM overwrites dvh, so it starts at dth)
+  DVLP_CUDA_OK(cudaMemsetAsync(ws + (tc ? L.dth : L.dvh), 0, L.pa - (tc ? L.dth : L.dvh), st));
   int prescaled = 0, dgt_swz = 0;
   {
-  ProfScope p(kProfBwd, st);
-  if (tc && tc_bwd_available()) {
+  if (tc) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
-    if (tc_bwd_version() == 2) {
+    {
+      ProfScope pb(kProfBwd, st);
       if ((rc = run_pair_bwd2(vb, tb, Bv, Bt, R, W, d, lambda, d_scores, ws, L, st))) return rc;
-      if ((rc = run_grad_gemm2(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
-      dgt_swz = 1;
-    } else {
-      if ((rc = run_pair_tc_bwd(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, d_scores, ws, L, st))) return rc;
-      if ((rc = run_grad_gemm(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
     }
+    {
+      ProfScope pg(kProfGG, st);
+      if ((rc = run_grad_gemm2(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
+    }
+    dgt_swz = 1;
     prescaled = 1;
   } else {
     PairArgs a{};
@@ -278,6 +267,7 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
     a.dvh = (float*)(ws + L.dvh); a.dth = (float*)(ws + L.dth);
     a.dgv = (float*)(ws + L.dgv); a.dgt = (float*)(ws + L.dgt);
     a.scratch = (float*)(ws + L.scratch); a.scratch_per_cta = L.scratch_per_cta;
+    ProfScope pb(kProfBwd, st);
     if ((rc = run_pair_generic(true, a, L.n_cta, st))) return rc;
   }
   }

@@ -58,7 +58,7 @@ __device__ __forceinline__ float leaky_grad(float x) { return x > 0.f ? 1.f : kL
 
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream
 // around the kernels of one slot.  Off by default; costs nothing when off.
-enum ProfSlot { kProfFwd = 0, kProfBwd = 1, kProfPrep = 2, kProfFinal = 3, kProfSlots = 4 };
+enum ProfSlot { kProfFwd = 0, kProfBwd = 1, kProfPrep = 2, kProfFinal = 3, kProfGG = 4, kProfSlots = 5 };
 struct ProfScope {
   int slot;
   cudaStream_t st;
@@ -85,8 +85,7 @@ struct Workspace {
   // backward accumulators
   size_t dvh, dth;           // fp32 (Bv,R,d), (Bt,W,d)
   size_t dgv, dgt;           // fp32 (Bv,R,R), (Bt,W,W)
-  size_t pa, pb;             // tcgen05 backward: bf16 P tiles (Bv * ceil(Bt/4), R, 128) spilled for grad_gemm.cu
-  size_t nrm_a, nrm_b;       // tcgen05: attention l2-norm factors per unit, (units,4,R) and (units,128), forward -> backward
+  size_t pa;                 // tcgen05 backward: bf16 gradient tiles P (Bv * ceil(Bt/4), 128 words, R) spilled for grad_gemm2.cu
   size_t rowv, colv;         // tcgen05: per-unit query scalars saved by the forward for pair_bwd2.cu: float4 (units,128) =
                              // (nB, thr1, 1/|c1|, cos1) per word, float4 (units,4,R) = (nA, thr2, 1/|c2|, cos2) per (text, region)
   size_t gbd;                // tcgen05: block-diagonal bf16 text Gram tiles (ceil(Bt/4), 128, 128)

@@ -33,7 +33,7 @@
 namespace dvlp {
 using namespace ptx;
 
-extern void* g_trace_buffer;   // pair_tc_bwd.cu (dvlp_debug_set_trace)
+extern void* g_trace_buffer;   // api.cu (dvlp_debug_set_trace)
 
 namespace tb2 {
 constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128;

@@ -60,8 +60,8 @@ uint64_t dvlp_launch_count(void);
 /*
  * Optional kernel timing for benchmarks: when enabled, CUDA events are recorded on the launching
  * stream around 0 = forward pair kernel, 1 = backward pair kernel, 2 = per-item prologue,
- * 3 = gradient finalisation.  dvlp_profile_read synchronises those events, writes the summed
- * milliseconds and launch-group counts of the four slots (ms[4], counts[4], HOST pointers) and resets.
+ * 3 = gradient finalisation, 4 = gradient GEMMs.  dvlp_profile_read synchronises those events, writes the
+ * summed milliseconds and launch-group counts of the five slots (ms[5], counts[5], HOST pointers) and resets.
  */
 void dvlp_profile_enable(int on);
 int dvlp_profile_read(double* ms_host, int* counts_host);

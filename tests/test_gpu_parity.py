@@ -264,3 +264,84 @@ def test_tcgen05_region_counts_and_ragged_text_tiles(shape):
         got = ops.rw_scores(d.im.to(torch.bfloat16), d.s.to(torch.bfloat16), d.im_mask, d.s_mask,
                             focal_equal=(focal == "equal"), impl="tcgen05")
         assert (got.cpu() - want).abs().max() < SCORE_TOL
+
+
+@pytest.mark.parametrize("shape", [(16, 32, 24), (16, 48, 12), (12, 64, 9), (9, 80, 7), (20, 80, 33)])
+def test_tcgen05_gradients_ragged_text_tiles(shape):
+    """Backward of the tcgen05 path (pair_bwd2.cu + grad_gemm2.cu) for every R instantiation with padded text
+    tiles, against the oracle's autograd on the same bf16-rounded inputs (gradients within 1e-2 relative)."""
+    Bv, R, Bt = shape
+    b = synth.make_batch(max(Bv, Bt), R, 32, 256, seed=23)
+    im = b.im[:Bv].to(torch.bfloat16)
+    s = b.s[:Bt].to(torch.bfloat16)
+    imm, sm = b.im_mask[:Bv].contiguous(), b.s_mask[:Bt].contiguous()
+    gen = torch.Generator().manual_seed(5)
+    w = torch.randn(Bv, Bt, generator=gen)
+    for focal in ("equal", "prob"):
+        ic = im.float().clone().requires_grad_(True)
+        sc = s.float().clone().requires_grad_(True)
+        (O.pair_scores(ic, sc, imm, sm, focal=focal) * w).sum().backward()
+        x = im.cuda().requires_grad_(True)
+        y = s.cuda().requires_grad_(True)
+        got = ops.rw_scores(x, y, imm.cuda(), sm.cuda(), focal_equal=(focal == "equal"), impl="tcgen05")
+        (got * w.cuda()).sum().backward()
+        assert x.grad.dtype == torch.bfloat16 and y.grad.dtype == torch.bfloat16
+        assert torch.isfinite(x.grad).all() and torch.isfinite(y.grad).all()
+        assert rel_err(x.grad.float().cpu(), ic.grad) < GRAD_TOL
+        assert rel_err(y.grad.float().cpu(), sc.grad) < GRAD_TOL
+
+
+def test_sim_matrix_bf16_tensor_core_path():
+    """bf16 CLS embeddings of width 256 take the mma.sync kernels (sim_mma.cu): exact products, fp32 norms,
+    gradients written in bf16."""
+    gen = torch.Generator().manual_seed(8)
+    for (n, m) in ((128, 128), (33, 70), (1000, 1000)):
+        a = torch.randn(n, 256, generator=gen).to(torch.bfloat16)
+        b = torch.randn(m, 256, generator=gen).to(torch.bfloat16)
+        a[0] = 0              # exercises the max(norm, eps) clamp
+        w = torch.randn(n, m, generator=gen)
+        ac = a.float().clone().requires_grad_(True)
+        bc = b.float().clone().requires_grad_(True)
+        want = O.sim_matrix(ac, bc)
+        (want * w).sum().backward()
+        x = a.cuda().requires_grad_(True)
+        y = b.cuda().requires_grad_(True)
+        got = L.sim_matrix(x, y)
+        (got * w.cuda()).sum().backward()
+        assert (got.detach().cpu() - want.detach()).abs().max() < 1e-5
+        assert x.grad.dtype == torch.bfloat16
+        assert rel_err(x.grad.float().cpu()[1:], ac.grad[1:]) < 5e-3      # bf16 rounding of the stored gradient
+        assert rel_err(y.grad.float().cpu(), bc.grad) < 5e-3
+
+
+def test_graphed_step_matches_eager():
+    """demovlp_b200.graph.GraphedLossStep: one CUDA-graph replay == the eager forward + backward."""
+    from demovlp_b200.graph import GraphedLossStep
+    b = synth.make_batch(32, 80, 32, 256, seed=31)
+    d = dev(b)
+    t = {"im": d.im.to(torch.bfloat16), "s": d.s.to(torch.bfloat16), "g_text": d.g_text.to(torch.bfloat16),
+         "g_vid": d.g_vid.to(torch.bfloat16), "im_mask": d.im_mask, "s_mask": d.s_mask}
+    mod = L.GlobalLocalLoss(focal_type="equal", coef=1.0)
+
+    def fn(x):
+        return mod(L.sim_matrix(x["g_text"], x["g_vid"]), x["im"], x["s"], x["im_mask"], d.s_len, x["s_mask"])
+
+    leaves = {k: t[k].detach().clone().requires_grad_(True) for k in ("im", "s", "g_text", "g_vid")}
+    out = fn({**t, **leaves})
+    out[0].backward()
+    gs = GraphedLossStep(fn, t, ("im", "s", "g_text", "g_vid"))
+    for _ in range(2):           # a replay is repeatable
+        losses = gs.replay()
+        torch.cuda.synchronize()
+        assert torch.allclose(losses.cpu(), torch.stack([o.detach().float() for o in out]).cpu(), rtol=1e-5, atol=1e-6)
+        for k in leaves:
+            assert rel_err(gs.grads[k].float().cpu(), leaves[k].grad.float().cpu()) < 1e-3
+    # new inputs through the static buffers
+    b2 = dev(synth.make_batch(32, 80, 32, 256, seed=32))
+    with torch.no_grad():
+        gs.inputs["im"].copy_(b2.im.to(torch.bfloat16))
+        gs.inputs["s"].copy_(b2.s.to(torch.bfloat16))
+    l2 = gs.replay().cpu()
+    t2 = {**t, "im": b2.im.to(torch.bfloat16), "s": b2.s.to(torch.bfloat16)}
+    want = fn(t2)
+    assert abs(float(l2[2]) - float(want[2])) < 1e-4
