@@ -4,6 +4,7 @@ rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, val = rows[0], rows[-1]
+print("kernel:", dict(zip(hdr, val)).get("Kernel Name", "?")[:100], "(last launch of the report)")
 want = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg,", "sm__inst_executed.sum.per_cycle_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum,", "dram__bytes_write.sum,", "launch__registers_per_thread,",
@@ -14,7 +15,10 @@ for h, v in zip(hdr, val):
         print(f"{h} = {v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]; data = rows[2:]
+# a report may hold several kernels: keep the last one's instruction table
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+rows = rows[starts[-1]:] if starts else rows
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
 idx = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = {s: 0 for s in stalls}
