@@ -403,8 +403,12 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Every collective of the run has completed (the last one is the all-reduce of the timings above).  Tearing the
+        # process group down while CUDA graphs that captured NCCL kernels are alive can block, so leave without it.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
