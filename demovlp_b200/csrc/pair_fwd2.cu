@@ -40,18 +40,17 @@ struct Lay {
   static constexpr int M2T = BETA + 512;            // [128]
   static constexpr int ALPHA = M2T + 512;           // [R]
   static constexpr int M2V = ALPHA + R * 4;         // [R]
-  static constexpr int TAB = M2V + R * 4;           // per compute warp [16] float4 (alpha, m2v, nA lam2, thr2)
-  static constexpr int P1 = TAB + NW * 256;         // [NC][128] row partials: sum l^2
-  static constexpr int P2 = P1 + NC * 512;          // [NC][128] row partials: sum e1
-  static constexpr int P3 = P2 + NC * 512;          // [NC][128] float2 row partials: num1, D1
-  static constexpr int T2I = P3 + NC * 1024;        // [NC][4] per-warp sums of cos2 over the warp's 16 regions
-  static constexpr int BARS = T2I + NC * 16;
+  static constexpr int TAB = M2V + R * 4;           // per compute warp [16] nA lam2, [16] thr2 of its columns
+  static constexpr int PART = TAB + NW * 128;       // [2][NC][128] float4 row partials (sum l^2, sum e1 | num1, D1 of the
+                                                    // previous tile), double-buffered by tile parity
+  static constexpr int T2I = PART + 2 * NC * 2048;  // [2][NC][4] per-warp sums of cos2 over the warp's 16 regions
+  static constexpr int BARS = T2I + 2 * NC * 16;
   static constexpr int TMEMPTR = BARS + 16 * 8;
   static constexpr int kAlloc = TMEMPTR + 16;
   static_assert(kAlloc <= 232448, "shared memory budget");
 };
 
-enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE0, S_DONE1, U_READY, Y_DONE, TILE_DONE, kNumBars };
+enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE0, S_DONE1, U_READY, Y_DONE, kNumBars };
 
 // TMEM columns: two S buffers, Y1, Y2
 constexpr uint32_t cS0 = 0, cS1 = 96, cY1 = 192, cY2 = 288;
@@ -116,7 +115,7 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     prefetch_tmap(&mapV); prefetch_tmap(&mapT); prefetch_tmap(&mapGV); prefetch_tmap(&mapGBD);
     for (int b = 0; b < kNumBars; ++b) {
       uint32_t cnt = 1;
-      if (b == VEC_FREE || b == U_READY || b == TILE_DONE) cnt = NW;
+      if (b == VEC_FREE || b == U_READY) cnt = NW;
       mbar_init(bar(b), cnt);
     }
     fence_mbar_init();
@@ -141,9 +140,9 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           // per-word vectors of the text tile: free once every warp has read its scalars
           if (k > 0) mbar_wait(bar(VEC_FREE), pp);
           if (k == 0 || jt == 0) {
-            // the resident video changes: every warp is done with tile k-1 (tables hold alpha / m2v copies, the
-            // S GEMM of tile k-1 read V, its Y1 GEMM read G^V)
-            if (k > 0) mbar_wait(bar(TILE_DONE), pp);
+            // the resident video changes: the S GEMM of tile k-1 read V, its Y1 GEMM read G^V, and every compute
+            // warp read alpha / m2v before it signalled U_READY for tile k-1, which the Y GEMMs waited for
+            if (k > 0) mbar_wait(bar(Y_DONE), pp);
             mbar_arrive_expect_tx(bar(V_FULL), 6 * L::kVChunk + 2 * R * 4);
             for (int c = 0; c < 4; ++c) tma_load_2d(sbase + L::V + c * L::kVChunk, &mapV, c * 64, i * R, bar(V_FULL));
             for (int c = 0; c < 2; ++c) tma_load_2d(sbase + L::GV + c * L::kVChunk, &mapGV, c * 64, i * R, bar(V_FULL));
@@ -226,153 +225,203 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     const uint32_t sw = (uint32_t)((m >> 2) & 1) << 4;
     const uint32_t row_off = (uint32_t)g * kCh32 + (uint32_t)m * 32;
     const uint32_t seg0 = row_off + sw, seg1 = row_off + (16u ^ sw);
-    float4* tab = reinterpret_cast<float4*>(sgen + L::TAB + cw * 256);
+    float* s_nal = reinterpret_cast<float*>(sgen + L::TAB + cw * 128);     // [16] nA * lam2 of this warp's columns
+    float* s_thr = s_nal + 16;                                               // [16] focal threshold of the t2i direction
     const float* s_beta = reinterpret_cast<const float*>(sgen + L::BETA);
     const float* s_m2t = reinterpret_cast<const float*>(sgen + L::M2T);
-    const float* s_alpha = reinterpret_cast<const float*>(sgen + L::ALPHA);
-    const float* s_m2v = reinterpret_cast<const float*>(sgen + L::M2V);
-    float* s_p1 = reinterpret_cast<float*>(sgen + L::P1);
-    float* s_p2 = reinterpret_cast<float*>(sgen + L::P2);
-    float2* s_p3 = reinterpret_cast<float2*>(sgen + L::P3);
+    const float4* s_alpha4 = reinterpret_cast<const float4*>(sgen + L::ALPHA) + g * 4;
+    const float4* s_m2v4 = reinterpret_cast<const float4*>(sgen + L::M2V) + g * 4;
+    float4* s_part = reinterpret_cast<float4*>(sgen + L::PART);
     float* s_t2i = reinterpret_cast<float*>(sgen + L::T2I);
     int vloads = 0, i = i0, jt = jt0;
+    // The last pass of a tile (Gram-form denominators, which need the Y GEMMs) is deferred into the next
+    // iteration, after that tile's first pass: the tensor-core round trip hides under it.  Carried state:
+    float num1_p = 0.f, num2_p = 0.f, nA_p = 0.f, thr2_p = 0.f, nB_p = 0.f, thr1_p = 0.f;
+    int i_p = 0, j_p = 0;
+    // deferred pass 3 of tile kp (Gram-form denominators, t2i cosines); returns this thread's D1 row partial.
+    // `par` = parity of the iteration it runs in (selects the exchange buffers)
+    auto deferred_pass = [&](int kp, uint32_t par) -> float {
+      float D1p = 0.f;
+      mbar_wait(bar(Y_DONE), kp & 1);
+      tc_fence_after();
+      uint32_t uw[8];                           // this thread's row segment of U1, then U2 (tile kp, still in place)
+      float y[16];
+      ld_shared_v4(sbase + L::U1 + seg0, uw[0], uw[1], uw[2], uw[3]);
+      ld_shared_v4(sbase + L::U1 + seg1, uw[4], uw[5], uw[6], uw[7]);
+      tmem_ld16(tmem + cY1 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
+      tmem_ld_wait();
+#pragma unroll
+      for (int p2 = 0; p2 < 8; ++p2) {
+        D1p = fmaf(bf16_lo(uw[p2]), y[2 * p2], D1p);
+        D1p = fmaf(bf16_hi(uw[p2]), y[2 * p2 + 1], D1p);
+      }
+      ld_shared_v4(sbase + L::U2 + seg0, uw[0], uw[1], uw[2], uw[3]);
+      ld_shared_v4(sbase + L::U2 + seg1, uw[4], uw[5], uw[6], uw[7]);
+      tmem_ld16(tmem + cY2 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
+      tmem_ld_wait();
+#pragma unroll
+      for (int p2 = 0; p2 < 8; ++p2) {
+        y[2 * p2] *= bf16_lo(uw[p2]);
+        y[2 * p2 + 1] *= bf16_hi(uw[p2]);
+      }
+      const float D2_cl = lanes_to_columns16(y, lane);
+      // t2i: cos2 of this warp's 16 (text, region) queries, summed over the regions (model/loss.py:326-327)
+      const float rden2 = D2_cl > 1e-30f ? rsqrtf(D2_cl) : 0.f;
+      float cos2 = num2_p * rden2;
+      if (a.colv && lane < 16)
+        a.colv[((size_t)(u0 + kp) * kTPT + q) * R + g * 16 + cl] = make_float4(nA_p, thr2_p, rden2, cos2);
+      cos2 += __shfl_xor_sync(0xffffffffu, cos2, 8);
+      cos2 += __shfl_xor_sync(0xffffffffu, cos2, 4);
+      cos2 += __shfl_xor_sync(0xffffffffu, cos2, 2);
+      cos2 += __shfl_xor_sync(0xffffffffu, cos2, 1);
+      if (lane == 0) s_t2i[(par * NC + g) * 4 + q] = cos2;
+      return D1p;
+    };
+    // i2t cosine of every word of tile kp (row totals n1 / d1 from the exchange), the pair score: warpgroup 0 only
+    auto finish_tile = [&](int kp, uint32_t par, float n1, float d1) {
+      const float rden1 = d1 > 1e-30f ? rsqrtf(d1) : 0.f;
+      float cs = n1 * rden1;
+      if (a.rowv) a.rowv[(size_t)(u0 + kp) * kRows + m] = make_float4(nB_p, thr1_p, rden1, cs);
+      cs = warp_sum(cs);                        // mean over the 32 words of text q (model/loss.py:318)
+      if (lane == 0 && j_p < a.Bt) {
+        float t2i = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < NC; ++gg) t2i += s_t2i[(par * NC + gg) * 4 + q];
+        a.scores[(size_t)i_p * a.Bt + j_p] = cs * (1.f / kW) + t2i * (1.f / R);
+      }
+    };
+
     for (int k = 0; k < n_tiles; ++k) {
       const uint32_t ph = k & 1;
-      const int j = jt * kTPT + q;
+      float x[16], eA[16];
+      float ssB = 0.f, sumA = 0.f;
       if (k == 0 || jt == 0) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
       mbar_wait(bar(VEC_FULL), ph);
       const float beta_m = s_beta[m], m2t_m = s_m2t[m];
-      if (lane < 16) tab[cl] = make_float4(s_alpha[g * 16 + cl], s_m2v[g * 16 + cl], 0.f, 0.f);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(VEC_FREE));
-
-      // ---------------- pass 0: S = raw alpha beta, the two query-axis l2 norms of model/loss.py:238 ----------------
+      // ------------- pass 0: S = raw alpha beta, the query-axis l2 norm of the i2t direction (model/loss.py:238) -------------
       mbar_wait(bar(S_DONE0 + ph), (k >> 1) & 1);
       tc_fence_after();
-      float x[16];
       tmem_ld16(tmem + (ph ? cS1 : cS0) + lane_off + g * 16, reinterpret_cast<uint32_t*>(x));
       tmem_ld_wait();
-      float nA_cl, nB;
+      float nA_cl;
       {
-        float sq[16], ssB = 0.f;
+        float sq[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          x[c] *= tab[c].x * beta_m;
-          const float l = leaky(x[c]);
-          sq[c] = l * l;
-          ssB += sq[c];
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 al = s_alpha4[c4];
+          const float av[4] = {al.x, al.y, al.z, al.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            x[c] *= av[e] * beta_m;
+            const float l = leaky(x[c]);
+            sq[c] = l * l;
+            ssB += sq[c];
+          }
         }
-        s_p1[g * kRows + m] = ssB;
-        const float ssA = lanes_to_columns16(sq, lane);      // sum over the 32 words of this text, column cl
+        const float ssA = lanes_to_columns16(sq, lane);        // sum over the 32 words of this text, column cl
         nA_cl = 1.f / (sqrtf(ssA) + kEps);
-        if (lane < 16) reinterpret_cast<float*>(tab + cl)[2] = nA_cl * a.lam2;
-        named_bar_sync(1 + q, 32 * NC);                      // row partials of the NC warps sharing this text slot
-        float tot = 0.f;
-#pragma unroll
-        for (int gg = 0; gg < NC; ++gg) tot += s_p1[gg * kRows + m];
-        nB = 1.f / (sqrtf(tot) + kEps);
+        if (lane < 16) s_nal[cl] = nA_cl * a.lam2;
       }
-      // ---------------- pass 1: exponentials, focal thresholds ----------------
-      float eA[16], eB[16];
-      float thr1, thr2_cl;
+      // ------------- deferred pass 3 of tile k-1 (its Y GEMMs ran under the pass above) -------------
+      float D1p = 0.f;
+      if (k > 0) D1p = deferred_pass(k - 1, ph);
+      // ------------- pass 1a: exponentials of the i2t direction (need only the lane-reduced norm) -------------
+      __syncwarp();                             // s_nal
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 nl = reinterpret_cast<const float4*>(s_nal)[c4];
+        const float4 mv = s_m2v4[c4];
+        const float nv[4] = {nl.x, nl.y, nl.z, nl.w}, mvv[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c4 * 4 + e;
+          eA[c] = ex2(fmaf(leaky(x[c]), nv[e], mvv[e]));
+          sumA += eA[c];
+        }
+      }
+      // ------------- the one exchange of row partials per tile (the NC warps that share this text slot) -------------
+      s_part[(ph * NC + g) * kRows + m] = make_float4(ssB, sumA, num1_p, D1p);
+      named_bar_sync(1 + q, 32 * NC);
+      float totB = 0.f, totA = 0.f, n1 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < NC; ++gg) {
+        const float4 pt = s_part[(ph * NC + gg) * kRows + m];
+        totB += pt.x; totA += pt.y; n1 += pt.z; d1 += pt.w;
+      }
+      if (k > 0 && g == 0) finish_tile(k - 1, ph, n1, d1);
+      // ------------- pass 1b: the t2i direction, focal thresholds -------------
+      const float nB = 1.f / (sqrtf(totB) + kEps);
+      const float thr1 = a.focal ? totA * (1.f / R) : -1.f;    // keep e iff e * R > sum_r e  (model/loss.py:280-282)
+      float eB[16];
+      float thr2_cl;
       {
         const float nBl = nB * a.lam2;
-        float sumA = 0.f, eb2[16];
+        float eb2[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float4 t = tab[c];              // alpha, m2v, nA lam2
-          const float l = leaky(x[c]);
-          eA[c] = ex2(fmaf(l, t.z, t.y));
-          eB[c] = ex2(fmaf(l, nBl, m2t_m));
-          sumA += eA[c];
+          eB[c] = ex2(fmaf(leaky(x[c]), nBl, m2t_m));
           eb2[c] = eB[c];
         }
-        s_p2[g * kRows + m] = sumA;
         const float sumB = lanes_to_columns16(eb2, lane);
-        thr2_cl = a.focal ? sumB * (1.f / kW) : -1.f;        // keep e iff e * W > sum_w e  (model/loss.py:280-282)
-        if (lane < 16) reinterpret_cast<float*>(tab + cl)[3] = thr2_cl;
-        named_bar_sync(1 + q, 32 * NC);
-        float tot = 0.f;
-#pragma unroll
-        for (int gg = 0; gg < NC; ++gg) tot += s_p2[gg * kRows + m];
-        thr1 = a.focal ? tot * (1.f / R) : -1.f;
+        thr2_cl = a.focal ? sumB * (1.f / kW) : -1.f;
+        if (lane < 16) s_thr[cl] = thr2_cl;
+        __syncwarp();
       }
-      // ---------------- pass 2: focal-selected u (bf16), operand tiles, numerators ----------------
-      uint32_t ub[16];                          // lo = u1 (i2t), hi = u2 (t2i)
-      float num1 = 0.f, num2_cl;
+      // ------------- pass 2: focal-selected u (bf16), operand tiles, numerators -------------
+      float num1 = 0.f;
       {
+        uint32_t w1[8], w2[8];
         float pn[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          ub[c] = pack_bf16(eA[c] > thr1 ? eA[c] : 0.f, eB[c] > tab[c].w ? eB[c] : 0.f);
-          num1 = fmaf(bf16_lo(ub[c]), x[c], num1);
-          pn[c] = bf16_hi(ub[c]) * x[c];
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 th = reinterpret_cast<const float4*>(s_thr)[c4];
+          const float tv[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const int c = c4 * 4 + e, p2 = c >> 1;
+            w1[p2] = pack_bf16(eA[c] > thr1 ? eA[c] : 0.f, eA[c + 1] > thr1 ? eA[c + 1] : 0.f);
+            w2[p2] = pack_bf16(eB[c] > tv[e] ? eB[c] : 0.f, eB[c + 1] > tv[e + 1] ? eB[c + 1] : 0.f);
+            num1 = fmaf(bf16_lo(w1[p2]), x[c], num1);
+            num1 = fmaf(bf16_hi(w1[p2]), x[c + 1], num1);
+            pn[c] = bf16_lo(w2[p2]) * x[c];
+            pn[c + 1] = bf16_hi(w2[p2]) * x[c + 1];
+          }
         }
-        if (k > 0) mbar_wait(bar(Y_DONE), (k - 1) & 1);      // the Y GEMMs of tile k-1 have read U1 / U2
-        st_shared_v4(sbase + L::U1 + seg0, prmt(ub[0], ub[1], 0x5410), prmt(ub[2], ub[3], 0x5410), prmt(ub[4], ub[5], 0x5410),
-                     prmt(ub[6], ub[7], 0x5410));
-        st_shared_v4(sbase + L::U1 + seg1, prmt(ub[8], ub[9], 0x5410), prmt(ub[10], ub[11], 0x5410),
-                     prmt(ub[12], ub[13], 0x5410), prmt(ub[14], ub[15], 0x5410));
-        st_shared_v4(sbase + L::U2 + seg0, prmt(ub[0], ub[1], 0x7632), prmt(ub[2], ub[3], 0x7632), prmt(ub[4], ub[5], 0x7632),
-                     prmt(ub[6], ub[7], 0x7632));
-        st_shared_v4(sbase + L::U2 + seg1, prmt(ub[8], ub[9], 0x7632), prmt(ub[10], ub[11], 0x7632),
-                     prmt(ub[12], ub[13], 0x7632), prmt(ub[14], ub[15], 0x7632));
+        // (the Y GEMMs of tile k-1 have read U1 / U2: waited for in the deferred pass above)
+        st_shared_v4(sbase + L::U1 + seg0, w1[0], w1[1], w1[2], w1[3]);
+        st_shared_v4(sbase + L::U1 + seg1, w1[4], w1[5], w1[6], w1[7]);
+        st_shared_v4(sbase + L::U2 + seg0, w2[0], w2[1], w2[2], w2[3]);
+        st_shared_v4(sbase + L::U2 + seg1, w2[4], w2[5], w2[6], w2[7]);
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(U_READY));
-        num2_cl = lanes_to_columns16(pn, lane);               // under the Y GEMMs
+        num2_p = lanes_to_columns16(pn, lane);                 // under the Y GEMMs
       }
-      // ---------------- pass 3: Gram-form denominators, cosines, score ----------------
-      mbar_wait(bar(Y_DONE), ph);
-      tc_fence_after();
-      float D1 = 0.f, D2_cl;
-      {
-        float y[16], pd[16];
-        tmem_ld16(tmem + cY1 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) D1 = fmaf(bf16_lo(ub[c]), y[c], D1);
-        tmem_ld16(tmem + cY2 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) pd[c] = bf16_hi(ub[c]) * y[c];
-        tc_fence_before();
-        D2_cl = lanes_to_columns16(pd, lane);
-      }
-      s_p3[g * kRows + m] = make_float2(num1, D1);
-      {
-        // t2i: cos2 of this warp's 16 (text, region) queries, summed over the regions (model/loss.py:326-327)
-        const float rden2 = D2_cl > 1e-30f ? rsqrtf(D2_cl) : 0.f;
-        float cos2 = num2_cl * rden2;
-        if (a.colv && lane < 16)
-          a.colv[((size_t)(u0 + k) * kTPT + q) * R + g * 16 + cl] = make_float4(nA_cl, thr2_cl, rden2, cos2);
-        cos2 += __shfl_xor_sync(0xffffffffu, cos2, 8);
-        cos2 += __shfl_xor_sync(0xffffffffu, cos2, 4);
-        cos2 += __shfl_xor_sync(0xffffffffu, cos2, 2);
-        cos2 += __shfl_xor_sync(0xffffffffu, cos2, 1);
-        if (lane == 0) s_t2i[g * 4 + q] = cos2;
-      }
-      named_bar_sync(1 + q, 32 * NC);
-      if (g == 0) {
-        float n = 0.f, d = 0.f;
-#pragma unroll
-        for (int gg = 0; gg < NC; ++gg) { const float2 p = s_p3[gg * kRows + m]; n += p.x; d += p.y; }
-        const float rden1 = d > 1e-30f ? rsqrtf(d) : 0.f;
-        float cs = n * rden1;
-        if (a.rowv) a.rowv[(size_t)(u0 + k) * kRows + m] = make_float4(nB, thr1, rden1, cs);
-        cs = warp_sum(cs);                      // mean over the 32 words of text q (model/loss.py:318)
-        if (lane == 0 && j < a.Bt) {
-          float t2i = 0.f;
-#pragma unroll
-          for (int gg = 0; gg < NC; ++gg) t2i += s_t2i[gg * 4 + q];
-          a.scores[(size_t)i * a.Bt + j] = cs * (1.f / kW) + t2i * (1.f / R);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(TILE_DONE));
+      num1_p = num1; nA_p = nA_cl; thr2_p = thr2_cl; nB_p = nB; thr1_p = thr1;
+      i_p = i; j_p = jt * kTPT + q;
       if (++jt == tpv) { jt = 0; ++i; }
     }
+    // ------------- the last tile's deferred pass -------------
+    {
+      const uint32_t par = n_tiles & 1;
+      const float D1p = deferred_pass(n_tiles - 1, par);
+      s_part[(par * NC + g) * kRows + m] = make_float4(0.f, 0.f, num1_p, D1p);
+      named_bar_sync(1 + q, 32 * NC);
+      if (g == 0) {
+        float n1 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < NC; ++gg) {
+          const float4 pt = s_part[(par * NC + gg) * kRows + m];
+          n1 += pt.z; d1 += pt.w;
+        }
+        finish_tile(n_tiles - 1, par, n1, d1);
+      }
+    }
+    tc_fence_before();
   }
 
   tc_fence_before();

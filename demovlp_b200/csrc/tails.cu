@@ -3,52 +3,104 @@
 //   NormSoftmaxLoss.forward  model/loss.py:126-138
 //   sim_matrix               model/model.py:582-590
 //   t2v_metrics / v2t_metrics rank search  model/metric.py:22-66, 142-189
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace dvlp {
 
 // ------------------------------------------------------------------ RWALoss
-// Single CTA (rows are few and short); deterministic reduction order.
-__global__ void __launch_bounds__(1024) k_rwa_loss(const float* __restrict__ scores, int n_rows, int n_cols,
-                                                   int row_offset, int n_total, float lambda,
-                                                   float* __restrict__ loss_sum, float* __restrict__ d_scores) {
+// One thread-block cluster of 8 CTAs (256 warps, one score row per warp at a time): rows are independent, the
+// per-CTA partial sums meet in CTA 0 through distributed shared memory in a fixed order (deterministic, no
+// scratch buffer, no atomics).  Rows of up to 1024 scores stay in registers between the passes.
+constexpr int kRwaCluster = 8;
+__global__ void __cluster_dims__(kRwaCluster, 1, 1) __launch_bounds__(1024)
+k_rwa_loss(const float* __restrict__ scores, int n_rows, int n_cols, int row_offset, int n_total, float lambda,
+           float* __restrict__ loss_sum, float* __restrict__ d_scores) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ float part[32];
+  __shared__ float cta_sum;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const float log_on = logf(1.f + 1e-6f), log_off = logf(1e-6f);   // torch.log(labels + 1e-6) in fp32
+  const float sc = lambda / (float)n_total;
   float acc = 0.f;
-  for (int i = warp; i < n_rows; i += nwarp) {
+  for (int i = blockIdx.x * nwarp + warp; i < n_rows; i += gridDim.x * nwarp) {
     const float* row = scores + (size_t)i * n_cols;
     const int tgt = i + row_offset;
-    float m = -INFINITY;
-    for (int j = lane; j < n_cols; j += 32) m = fmaxf(m, lambda * row[j]);
-    m = warp_max(m);
-    float se = 0.f;
-    for (int j = lane; j < n_cols; j += 32) se += expf(lambda * row[j] - m);
-    se = warp_sum(se);
-    const float lse = m + logf(se);
-    float kl = 0.f;
-    for (int j = lane; j < n_cols; j += 32) {
-      float logp = lambda * row[j] - lse;
-      kl += expf(logp) * (logp - (j == tgt ? log_on : log_off));
-    }
-    kl = warp_sum(kl);
-    if (d_scores) {
-      const float sc = lambda / (float)n_total;
-      for (int j = lane; j < n_cols; j += 32) {
-        float logp = lambda * row[j] - lse;
-        float gg = logp - (j == tgt ? log_on : log_off);
-        d_scores[(size_t)i * n_cols + j] = sc * expf(logp) * (gg - kl);
+    if (n_cols <= 1024) {
+      float z[32];
+      float m = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const int j = lane + 32 * t;
+        z[t] = j < n_cols ? lambda * row[j] : -INFINITY;
+        m = fmaxf(m, z[t]);
       }
+      m = warp_max(m);
+      float se = 0.f;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) se += (lane + 32 * t < n_cols) ? expf(z[t] - m) : 0.f;
+      se = warp_sum(se);
+      const float lse = m + logf(se);
+      float kl = 0.f;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const int j = lane + 32 * t;
+        if (j < n_cols) {
+          const float logp = z[t] - lse;
+          kl += expf(logp) * (logp - (j == tgt ? log_on : log_off));
+        }
+      }
+      kl = warp_sum(kl);
+      if (d_scores) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int j = lane + 32 * t;
+          if (j < n_cols) {
+            const float logp = z[t] - lse;
+            d_scores[(size_t)i * n_cols + j] = sc * expf(logp) * ((logp - (j == tgt ? log_on : log_off)) - kl);
+          }
+        }
+      }
+      acc += kl;   // identical in all lanes
+    } else {
+      float m = -INFINITY;
+      for (int j = lane; j < n_cols; j += 32) m = fmaxf(m, lambda * row[j]);
+      m = warp_max(m);
+      float se = 0.f;
+      for (int j = lane; j < n_cols; j += 32) se += expf(lambda * row[j] - m);
+      se = warp_sum(se);
+      const float lse = m + logf(se);
+      float kl = 0.f;
+      for (int j = lane; j < n_cols; j += 32) {
+        const float logp = lambda * row[j] - lse;
+        kl += expf(logp) * (logp - (j == tgt ? log_on : log_off));
+      }
+      kl = warp_sum(kl);
+      if (d_scores) {
+        for (int j = lane; j < n_cols; j += 32) {
+          const float logp = lambda * row[j] - lse;
+          d_scores[(size_t)i * n_cols + j] = sc * expf(logp) * ((logp - (j == tgt ? log_on : log_off)) - kl);
+        }
+      }
+      acc += kl;
     }
-    acc += kl;   // identical in all lanes
   }
   if (lane == 0) part[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < nwarp; ++w) t += part[w];
+    cta_sum = t;
+  }
+  cluster.sync();
+  if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+    float t = 0.f;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) t += *cluster.map_shared_rank(&cta_sum, r);
     *loss_sum = t / (float)n_total;
   }
+  cluster.sync();      // remote shared memory must outlive the reads above
 }
 
 // ---------------------------------------------------------- NormSoftmaxLoss
@@ -106,6 +158,67 @@ __global__ void k_ns_grad(const float* __restrict__ x, int N, int M, float inv_t
   if (i < n) g += expf(z - lse_r[i]) - diag;
   if (j < n) g += expf(z - lse_c[j]) - diag;
   d_x[e] = g * inv_t / (float)n;
+}
+
+// Small matrices (per-GPU batch: N, M <= 256): the four steps above in ONE launch.  A cluster of 8 CTAs computes
+// the row / column log-sum-exps (one warp each), meets at a cluster barrier and then writes the loss (CTA 0) and
+// the gradient (all CTAs); lse_r / lse_c travel through the caller's scratch buffer (L2).
+constexpr int kNsCluster = 8;
+__global__ void __cluster_dims__(kNsCluster, 1, 1) __launch_bounds__(1024)
+k_ns_small(const float* __restrict__ x, int N, int M, float inv_t, float* lse, float* __restrict__ loss,
+           float* __restrict__ d_x) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float part[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int idx = blockIdx.x * nwarp + warp; idx < N + M; idx += gridDim.x * nwarp) {
+    float m = -INFINITY, se = 0.f;
+    if (idx < N) {
+      const float* row = x + (size_t)idx * M;
+      for (int j = lane; j < M; j += 32) m = fmaxf(m, row[j] * inv_t);
+      m = warp_max(m);
+      for (int j = lane; j < M; j += 32) se += expf(row[j] * inv_t - m);
+    } else {
+      const int j = idx - N;
+      for (int i = lane; i < N; i += 32) m = fmaxf(m, x[(size_t)i * M + j] * inv_t);
+      m = warp_max(m);
+      for (int i = lane; i < N; i += 32) se += expf(x[(size_t)i * M + j] * inv_t - m);
+    }
+    se = warp_sum(se);
+    if (lane == 0) lse[idx] = m + logf(se);
+  }
+  __threadfence();
+  cluster.sync();
+  const float* lse_r = lse;
+  const float* lse_c = lse + N;
+  const int n = N < M ? N : M;
+  if (blockIdx.x == 0) {
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float z = x[(size_t)i * M + i] * inv_t;
+      a += (z - __ldcg(lse_r + i)) + (z - __ldcg(lse_c + i));
+    }
+    a = warp_sum(a);
+    if (lane == 0) part[warp] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < nwarp; ++w) t += part[w];
+      *loss = -t / (float)n;
+    }
+  }
+  if (d_x) {
+    const size_t total = (size_t)N * M;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+      const int i = (int)(e / M), j = (int)(e - (size_t)i * M);
+      const float z = x[e] * inv_t;
+      const float diag = (i == j) ? 1.f : 0.f;
+      float g = 0.f;
+      if (i < n) g += expf(z - __ldcg(lse_r + i)) - diag;
+      if (j < n) g += expf(z - __ldcg(lse_c + j)) - diag;
+      d_x[e] = g * inv_t / (float)n;
+    }
+  }
 }
 
 // --------------------------------------------------------------- sim_matrix
@@ -274,7 +387,7 @@ __global__ void __launch_bounds__(256) k_ranks_v2t(const double* __restrict__ si
 // ------------------------------------------------------------ host wrappers
 int run_rwa_loss(const float* scores, int n_rows, int n_cols, int row_offset, int n_total, float lambda,
                  float* loss_sum, float* d_scores, cudaStream_t st) {
-  k_rwa_loss<<<1, 1024, 0, st>>>(scores, n_rows, n_cols, row_offset, n_total, lambda, loss_sum, d_scores);
+  k_rwa_loss<<<kRwaCluster, 1024, 0, st>>>(scores, n_rows, n_cols, row_offset, n_total, lambda, loss_sum, d_scores);
   DVLP_LAUNCH_OK();
   return DVLP_OK;
 }
@@ -284,6 +397,11 @@ int run_normsoftmax(const float* x, int N, int M, float temperature, float* loss
   const float inv_t = 1.f / temperature;
   float* lr = scratch;
   float* lc = scratch + N;
+  if (N <= 256 && M <= 256) {
+    k_ns_small<<<kNsCluster, 1024, 0, st>>>(x, N, M, inv_t, scratch, loss, d_x);
+    DVLP_LAUNCH_OK();
+    return DVLP_OK;
+  }
   k_lse_rows<<<(N + 7) / 8, 256, 0, st>>>(x, N, M, inv_t, lr);
   DVLP_LAUNCH_OK();
   k_lse_cols<<<(M + 7) / 8, 256, 0, st>>>(x, N, M, inv_t, lc);
