@@ -90,7 +90,7 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
   const uint32_t tmem = *s_tmem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int k = 0; k < n_steps; ++k) {
         const int s = k % kStages, it = k / kStages;
         if (it > 0) mbar_wait(empty(s), (it - 1) & 1);
@@ -115,7 +115,7 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
       const int s = k % kStages, it = k / kStages;
       mbar_wait(full(s), it & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = sbase + s * L::STAGE;
         if (MODE == MODE_V) {
           // K = 128 words: P rows are the K rows of an MN-major operand whose M (regions) chunks are 4 KB apart;

@@ -86,7 +86,7 @@ struct Args {
 // trace slot layout: [role 0..4][tile 0..31][event 0..15]; roles: 1 = MMA warp, 2 = compute warp (g0,q0), 3 = (g4,q3)
 #define TR2(role, ev)                                                                        \
   do {                                                                                      \
-    if (a.trace && blockIdx.x == 0 && lane == 0 && k < 32) a.trace[((role) * 32 + k) * 16 + (ev)] = clock64(); \
+    if (TRACE && a.trace && blockIdx.x == 0 && lane == 0 && k < 32) a.trace[((role) * 32 + k) * 16 + (ev)] = clock64(); \
   } while (0)
 #define TRC(ev) do { if (cw == 0) TR2(2, ev); else if (cw == NW - 1) TR2(3, ev); } while (0)
 
@@ -116,7 +116,7 @@ __device__ __forceinline__ float lanes_to_columns16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-template <int R>
+template <int R, bool TRACE>
 __global__ void __launch_bounds__(Lay<R>::kThreads, 1)
 k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapT,
             const __grid_constant__ CUtensorMap mapGV, const __grid_constant__ CUtensorMap mapGBD,
@@ -161,7 +161,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     if (NC == 5) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
       // =============================== TMA producer ===============================
-      if (lane == 0) {
+      if (elect_one()) {
         int i = i0, jt = jt0;
         for (int k = 0; k < n_tiles; ++k) {
           const uint32_t pp = (k - 1) & 1;
@@ -209,7 +209,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         if (sw) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
         mbar_wait(bar(T_FULL), k & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 16; ++ks) {
             const uint32_t oT = ((ks >> 2) * kTileBytes + (ks & 3) * 32) >> 4, oV = ((ks >> 2) * CH + (ks & 3) * 32) >> 4;
@@ -228,7 +228,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         mbar_wait(bar(U_READY), ph);
         tc_fence_after();
         TR2(1, 0);
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < NC; ++ks)
             mma_bf16_w(tmem + cY1, loU1k + ((ks * kCh32) >> 4), hi32, loGV + (((ks >> 2) * CH + (ks & 3) * 32) >> 4), hi128,
@@ -242,7 +242,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         __syncwarp();
         // ---- dGV += UD1^T U1 (K = 128 words),  dGT = UD2 U2^T (K = R regions): UD was written with U
         TR2(1, 1);
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             mma_bf16_w(tmem + cDGV, loUD1m + ((ks * 512) >> 4), hi32, loU1m + ((ks * 512) >> 4), hi32, idDGV,
@@ -260,7 +260,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       }
     } else if (warp == 2) {
       // ====== stores: the bf16 gradient tile P of each unit (TMA tile store) and its dG^T block (bulk add) ======
-      if (lane == 0) {
+      if (elect_one()) {
         int jt = jt0;
         for (int k = 0; k < n_tiles; ++k) {
           mbar_wait(bar(P_READY), k & 1);
@@ -312,6 +312,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       const uint32_t ph = k & 1;
       const int j = jt * kTPT + q;
       const bool last_of_video = (k == n_tiles - 1) || (jt == tpv - 1);
+      TRC(11);
       const float gs = gs_next;
       if (k + 1 < n_tiles) gs_next = (jt + 1 == tpv) ? load_g(i + 1, 0) : load_g(i, jt + 1);   // one tile ahead
       TRC(0);
@@ -329,7 +330,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         const float c1B = gs * (1.f / R) * cv.z, kapB = cv.w * cv.z;
         nA_cl = cv.x;
         if (lane < 16) {
-          tab[cl] = make_float4(cv.x, cv.y, al, mv);                          // phase 1: nA, thr2, alpha, m2v
+          tab[cl] = make_float4(cv.x * a.lam2, cv.y, al, mv);                 // phase 1: nA lam2, thr2, alpha, m2v
           tab[16 + cl] = make_float4(a.lam * c1B, kapB, cv.x, c1B);          // phase 2: lambda c1B, kapB, nA, c1B
           tab[32 + cl] = make_float4(0.f, al, -0.5f * c1B * kapB, 0.f);      // phase 3: nA^2 tA, alpha | phase 1: dDB
         }
@@ -338,7 +339,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(bar(VEC_FREE));
       const float nB = rv.x;
       const float c1A = gs * (1.f / kW) * rv.z, kapA = rv.w * rv.z;
-      const float lc1A = a.lam * c1A;
+      const float lc1A = a.lam * c1A, inv_lam = 1.f / a.lam;
 
       // -------------- phase 1: recompute u1, u2; U = u and UD = u dD operand tiles --------------
       mbar_wait(bar(S_DONE), ph);
@@ -355,7 +356,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           const float4 t1 = tab[c];
           x[c] *= t1.z * beta_m;
           const float l = leaky(x[c]);
-          const float eA = ex2(fmaf(l * t1.x, a.lam2, t1.w));
+          const float eA = ex2(fmaf(l, t1.x, t1.w));
           const float eB = ex2(fmaf(l, nBl, m2t_m));
           ub[c] = pack_bf16(eA > thr1 ? eA : 0.f, eB > t1.y ? eB : 0.f);
         }
@@ -399,38 +400,44 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         float p8[8];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          float y1[8], y2[8], Qh[8];
           uint32_t ua[4], ubb[4];
           const uint32_t so = half ? seg1 : seg0;
-          tmem_ld8(tmem + cY1 + lane_off + g * 16 + half * 8, reinterpret_cast<uint32_t*>(y1));
-          tmem_ld8(tmem + cY2 + lane_off + g * 16 + half * 8, reinterpret_cast<uint32_t*>(y2));
           ld_shared_v4(sbase + L::U1 + so, ua[0], ua[1], ua[2], ua[3]);
           ld_shared_v4(sbase + L::U2 + so, ubb[0], ubb[1], ubb[2], ubb[3]);
-          tmem_ld_wait();
 #pragma unroll
-          for (int c2 = 0; c2 < 8; c2 += 2) {
-            float pa[2];
+          for (int qt = 0; qt < 2; ++qt) {      // quarters of 4 columns keep the register footprint below the cap
+            float y1[4], y2[4], Qh[4];
+            const uint32_t col = g * 16 + half * 8 + qt * 4;
+            tmem_ld4(tmem + cY1 + lane_off + col, reinterpret_cast<uint32_t*>(y1));
+            tmem_ld4(tmem + cY2 + lane_off + col, reinterpret_cast<uint32_t*>(y2));
+            tmem_ld_wait();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int cc = half * 8 + c2 + h;
-              const float4 t2 = tab[16 + cc];   // lambda c1B, kapB, nA, c1B
-              const float xv = x[cc], l = leaky(xv);
-              const float uA = h ? bf16_hi(ua[c2 >> 1]) : bf16_lo(ua[c2 >> 1]);
-              const float uB = h ? bf16_hi(ubb[c2 >> 1]) : bf16_lo(ubb[c2 >> 1]);
-              const float dAA = lc1A * uA * fmaf(-kapA, y1[c2 + h], xv);
-              const float dAB = t2.x * uB * fmaf(-t2.y, y2[c2 + h], xv);
-              const float E = dAA * t2.z, F = dAB * nB;
-              const float hh = fmaf(c1A, uA, t2.w * uB);
-              pa[h] = l * E;
-              tB = fmaf(l, F, tB);
-              Qh[c2 + h] = (E + F) + (xv > 0.f ? hh : 10.f * hh);
+            for (int c2 = 0; c2 < 4; c2 += 2) {
+              float pa[2];
+              const int w = qt * 2 + (c2 >> 1);   // bf16 pair holding these two columns
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int cc = half * 8 + qt * 4 + c2 + h;
+                const float4 t2 = tab[16 + cc];   // lambda c1B, kapB, nA
+                const float xv = x[cc], l = leaky(xv);
+                const float uA = h ? bf16_hi(ua[w]) : bf16_lo(ua[w]);
+                const float uB = h ? bf16_hi(ubb[w]) : bf16_lo(ubb[w]);
+                // dA = lambda c1 u (S - kap Y); the factors that are constant along a reduction axis (nA along the
+                // words, nB along the regions) are applied after the sums
+                const float gA0 = lc1A * uA, gB0 = t2.x * uB;
+                const float G = gA0 * fmaf(-kapA, y1[c2 + h], xv);
+                const float F = gB0 * fmaf(-t2.y, y2[c2 + h], xv);
+                pa[h] = l * G;
+                tB = fmaf(l, F, tB);
+                Qh[c2 + h] = fmaf(gA0 + gB0, xv > 0.f ? inv_lam : 10.f * inv_lam, fmaf(t2.z, G, nB * F));
+              }
+              // first butterfly step (lane bit 0 <-> column bit 0) of the lanes->columns reduction of A1 dA1
+              const bool up1 = (lane & 1) != 0;
+              const float send = up1 ? pa[0] : pa[1], keep = up1 ? pa[1] : pa[0];
+              p8[(half * 8 + qt * 4 + c2) >> 1] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
             }
-            // first butterfly step (lane bit 0 <-> column bit 0) of the lanes->columns reduction of A1 dA1
-            const bool up1 = (lane & 1) != 0;
-            const float send = up1 ? pa[0] : pa[1], keep = up1 ? pa[1] : pa[0];
-            p8[(half * 8 + c2) >> 1] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            tmem_st4(tmem + cY1 + lane_off + col, reinterpret_cast<const uint32_t*>(Qh));
           }
-          tmem_st8(tmem + cY1 + lane_off + g * 16 + half * 8, reinterpret_cast<const uint32_t*>(Qh));
         }
         // remaining steps: p8[e] holds column 2e + (lane & 1); lane bit h <-> column bit h
 #pragma unroll
@@ -447,14 +454,14 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       }
       tc_fence_before();
       s_tbp[g * kRows + m] = tB;
-      if (lane < 16) reinterpret_cast<float*>(tab + 32 + cl)[0] = nA_cl * nA_cl * tA;
+      if (lane < 16) reinterpret_cast<float*>(tab + 32 + cl)[0] = nA_cl * nA_cl * nA_cl * tA;
       TRC(5);
       named_bar_sync(1 + q, 32 * NC);           // the NC warps that share this text slot
       TRC(6);
       float zB = 0.f;
 #pragma unroll
       for (int gg = 0; gg < NC; ++gg) zB += s_tbp[gg * kRows + m];
-      zB *= nB * nB;
+      zB *= nB * nB * nB;
 
       // ------------------------------ phase 3: dS, P ------------------------------
       uint32_t pk[8];
@@ -589,10 +596,14 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, float lambda, 
   int grid = (int)(a.total_units < sms ? a.total_units : sms);
   static bool attr_set = false;
   if (!attr_set) {
-    DVLP_CUDA_OK(cudaFuncSetAttribute(k_pair_bwd2<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_pair_bwd2<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_pair_bwd2<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
     attr_set = true;
   }
-  k_pair_bwd2<R><<<grid, L::kThreads, L::kAlloc, st>>>(mV, mT, mGV, mGBD, mP, a);
+  if (a.trace)      // debugging aid (tools/trace_tiles.py): the instrumented instantiation
+    k_pair_bwd2<R, true><<<grid, L::kThreads, L::kAlloc, st>>>(mV, mT, mGV, mGBD, mP, a);
+  else
+    k_pair_bwd2<R, false><<<grid, L::kThreads, L::kAlloc, st>>>(mV, mT, mGV, mGBD, mP, a);
   DVLP_LAUNCH_OK();
   return DVLP_OK;
 }

@@ -133,7 +133,7 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     if (NC == 5) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
       // =============================== TMA producer ===============================
-      if (lane == 0) {
+      if (elect_one()) {
         int i = i0, jt = jt0;
         for (int k = 0; k < n_tiles; ++k) {
           const uint32_t pp = (k - 1) & 1;
@@ -176,7 +176,7 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         if (sw) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
         mbar_wait(bar(T_FULL), k & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t dS = tmem + ((k & 1) ? cS1 : cS0);
 #pragma unroll
           for (int ks = 0; ks < 16; ++ks) {
@@ -199,7 +199,7 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         mbar_wait(bar(GBD_FULL), ph);
         mbar_wait(bar(U_READY), ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < NC; ++ks)
             mma_bf16_w(tmem + cY1, loU1k + ((ks * kCh32) >> 4), hi32, loGV + (((ks >> 2) * CH + (ks & 3) * 32) >> 4), hi128,

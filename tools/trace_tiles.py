@@ -17,7 +17,7 @@ else:   # pair_bwd2.cu
     ROLES = ["tma", "mma", "cw(g0,q0)", "cw(last)", "-"]
     EV_MMA = ["U ready", "Y issued", "UD ready", "dG issued", "next S issued"]
     EV_GRP = ["start", "vec full", "S done", "U arrive", "Y done", "UD arrive", "tB bar", "P computed", "dG done",
-              "P arrive", "flushed"]
+              "P arrive", "flushed", "loop top"]
 
 
 def main():
