@@ -60,6 +60,27 @@ def gather_cat(t, group=None):
     return out
 
 
+def gather_cat_many(tensors, group=None):
+    """gather_cat of several tensors as ONE collective launch where the backend can group them.
+
+    With NCCL the all-gathers are issued inside one group (c10d's coalescing manager): one kernel launch and one
+    synchronisation instead of one per tensor -- at the sizes of this path (a few MiB) every collective is
+    latency-bound, so the launch count is what matters.  Other backends (gloo in the CPU tests) fall back to
+    one call per tensor."""
+    world = dist.get_world_size(group)
+    ins = [t.contiguous() for t in tensors]
+    outs = [torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in ins]
+    coalesce = getattr(dist, "_coalescing_manager", None)
+    if coalesce is not None and len(ins) > 1 and ins[0].is_cuda and dist.get_backend(group) == "nccl":
+        with coalesce(group=group, device=ins[0].device, async_ops=False):
+            for o, t in zip(outs, ins):
+                dist.all_gather_into_tensor(o, t, group=group)
+    else:
+        for o, t in zip(outs, ins):
+            dist.all_gather_into_tensor(o, t, group=group)
+    return outs
+
+
 class AllGather_multi(torch.autograd.Function):
     """Drop-in for trainer/trainer_dist.py:13-31: ``AllGather_multi.apply(tensor, n_gpu, args)``.
 
@@ -81,30 +102,33 @@ class AllGather_multi(torch.autograd.Function):
 
 
 class _GatherRows(torch.autograd.Function):
-    """Same as AllGather_multi but bound to a process group instead of an args namespace."""
+    """Same as AllGather_multi but bound to a process group instead of an args namespace.
+    ``gathered`` (optional) is the result of an all-gather that has already been done (gather_cat_many)."""
 
     @staticmethod
-    def forward(ctx, tensor, group):
+    def forward(ctx, tensor, group, gathered=None):
         ctx.rank = dist.get_rank(group)
         ctx.b = tensor.shape[0]
-        return gather_cat(tensor, group)
+        return gather_cat(tensor, group) if gathered is None else gathered.view_as(gathered)
 
     @staticmethod
     def backward(ctx, g):
-        return g[ctx.b * ctx.rank:ctx.b * (ctx.rank + 1)], None
+        return g[ctx.b * ctx.rank:ctx.b * (ctx.rank + 1)], None, None
 
 
 class _ShardedRWA(torch.autograd.Function):
     """local_loss of the concatenated batch from row shards (model/loss.py:105-116 on P ranks)."""
 
     @staticmethod
-    def forward(ctx, im, s, im_m, s_m, lam, focal_equal, impl, group):
+    def forward(ctx, im, s, im_m, s_m, lam, focal_equal, impl, group, pre=None):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         b = s.shape[0]
         if im.shape[0] != b:
             raise RuntimeError("sharded RWALoss needs the same number of videos and texts per rank")
-        s_all = gather_cat(s.detach(), group)               # (B, W, d): the only embedding that moves
-        s_m_all = gather_cat(s_m.detach().to(torch.float32), group)
+        if pre is None:                                     # (B, W, d): the only embedding that moves
+            s_all, s_m_all = gather_cat_many([s.detach(), s_m.detach().to(torch.float32)], group)
+        else:
+            s_all, s_m_all = pre
         scores, state = _BACKEND.scores_fwd(im.detach(), s_all, im_m, s_m_all, lam, focal_equal, impl)
         want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         part, d_scores = _BACKEND.rwa_tail(scores, lam, rank * b, world * b, want)
@@ -122,7 +146,7 @@ class _ShardedRWA(torch.autograd.Function):
         # every rank holds a partial gradient for ALL texts: sum and hand each rank its rows
         d_s = torch.empty((ctx.b,) + tuple(d_s_all.shape[1:]), dtype=d_s_all.dtype, device=d_s_all.device)
         dist.reduce_scatter_tensor(d_s, d_s_all.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
-        return d_im.to(ctx.dtypes[0]), d_s.to(ctx.dtypes[1]), None, None, None, None, None, None
+        return d_im.to(ctx.dtypes[0]), d_s.to(ctx.dtypes[1]), None, None, None, None, None, None, None
 
 
 class ShardedGlobalLocalLoss(nn.Module):
@@ -148,14 +172,16 @@ class ShardedGlobalLocalLoss(nn.Module):
         self.group = group
         self.impl = impl
 
-    def global_part(self, text_cls, video_cls):
-        t_all = _GatherRows.apply(text_cls, self.group)
-        v_all = _GatherRows.apply(video_cls, self.group)
+    def global_part(self, text_cls, video_cls, pre=None):
+        if pre is None:
+            pre = gather_cat_many([text_cls.detach(), video_cls.detach()], self.group)
+        t_all = _GatherRows.apply(text_cls, self.group, pre[0])
+        v_all = _GatherRows.apply(video_cls, self.group, pre[1])
         return _BACKEND.norm_softmax(_BACKEND.sim_matrix(t_all, v_all), self.temperature)
 
-    def local_part(self, im, s, im_m, s_m):
+    def local_part(self, im, s, im_m, s_m, pre=None):
         return _ShardedRWA.apply(im, s, im_m, s_m, self.lambda_softmax, self.focal_type == "equal",
-                                 self.impl, self.group)
+                                 self.impl, self.group, pre)
 
     def forward(self, global_pair, local_im, local_s, local_im_m, local_s_l, local_s_m):
         zero = torch.tensor([0.0])
@@ -165,6 +191,10 @@ class ShardedGlobalLocalLoss(nn.Module):
         if not self.use_global:
             l = self.local_part(local_im, local_s, local_im_m, local_s_m)
             return l, zero, l
-        g = self.global_part(*global_pair)
-        l = self.local_part(local_im, local_s, local_im_m, local_s_m)
+        # everything that moves in the forward (text embeddings + masks, both CLS matrices) in ONE grouped all-gather
+        t_all, v_all, s_all, s_m_all = gather_cat_many(
+            [global_pair[0].detach(), global_pair[1].detach(), local_s.detach(),
+             local_s_m.detach().to(torch.float32)], self.group)
+        g = self.global_part(*global_pair, pre=(t_all, v_all))
+        l = self.local_part(local_im, local_s, local_im_m, local_s_m, pre=(s_all, s_m_all))
         return g + l, g, l
