@@ -37,6 +37,10 @@ SYMBOLS = {
     "dvlp_normsoftmax_fwd_bwd": (_i, [_p, _i, _i, _f, _p, _p, _p, _p]),
     "dvlp_ranks_t2v": (_i, [_p, _i, _i, _p, _p]),
     "dvlp_ranks_v2t": (_i, [_p, _i, _i, _p, _p]),
+    "dvlp_p2p_control_bytes": (_sz, []),
+    "dvlp_p2p_allgather": (_i, [_p, _i, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _p]),
+    "dvlp_p2p_sum_scalar": (_i, [_p, _i, _i, _p, _p, _p]),
+    "dvlp_p2p_reduce_scatter": (_i, [_p, _i, _i, _sz, _sz, _p, _i, _p]),
 }
 
 _lib = None

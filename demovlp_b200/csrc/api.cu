@@ -47,6 +47,9 @@ int run_sim_bwd(const void*, const void*, int, int, int, float, int, const float
                 cudaStream_t);
 int run_ranks_t2v(const double*, int, int, int32_t*, cudaStream_t);
 int run_ranks_v2t(const double*, int, int, double*, cudaStream_t);
+int run_p2p_allgather(void* const*, int, int, int, const void* const*, const size_t*, const size_t*, cudaStream_t);
+int run_p2p_sum_scalar(void* const*, int, int, const float*, float*, cudaStream_t);
+int run_p2p_reduce_scatter(void* const*, int, int, size_t, size_t, void*, int, cudaStream_t);
 // tcgen05 path: pair_fwd2.cu, pair_bwd2.cu, grad_gemm2.cu
 int run_pair_fwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
                   float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
@@ -342,6 +345,46 @@ int dvlp_ranks_v2t(const double* sims, int Nq, int Nv, double* ranks, void* stre
   int rc = device_ok();
   if (rc) return rc;
   return run_ranks_v2t(sims, Nq, Nv, ranks, (cudaStream_t)stream);
+}
+
+size_t dvlp_p2p_control_bytes(void) { return 4096; }
+
+int dvlp_p2p_allgather(void* const* peer_arenas, int world, int rank, int n_tensors, const void* const* shards_host,
+                       const size_t* shard_bytes_host, const size_t* arena_offsets_host, void* stream) {
+  if (!peer_arenas || !shards_host || !shard_bytes_host || !arena_offsets_host) return DVLP_ERR_NULL_POINTER;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world || n_tensors < 1 || n_tensors > 8) return DVLP_ERR_BAD_ARG;
+  for (int t = 0; t < n_tensors; ++t) {
+    if (!shards_host[t]) return DVLP_ERR_NULL_POINTER;
+    if (shard_bytes_host[t] == 0 || (shard_bytes_host[t] & 15) || (arena_offsets_host[t] & 15) ||
+        ((uintptr_t)shards_host[t] & 15))
+      return DVLP_ERR_MISALIGNED;
+    if (arena_offsets_host[t] < dvlp_p2p_control_bytes()) return DVLP_ERR_BAD_ARG;
+  }
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_p2p_allgather(peer_arenas, world, rank, n_tensors, shards_host, shard_bytes_host, arena_offsets_host,
+                           (cudaStream_t)stream);
+}
+
+int dvlp_p2p_sum_scalar(void* const* peer_arenas, int world, int rank, const float* value, float* out, void* stream) {
+  if (!peer_arenas || !value || !out) return DVLP_ERR_NULL_POINTER;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return DVLP_ERR_BAD_ARG;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_p2p_sum_scalar(peer_arenas, world, rank, value, out, (cudaStream_t)stream);
+}
+
+int dvlp_p2p_reduce_scatter(void* const* peer_arenas, int world, int rank, size_t arena_offset, size_t shard_floats,
+                            void* out, int out_dtype, void* stream) {
+  if (!peer_arenas || !out) return DVLP_ERR_NULL_POINTER;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return DVLP_ERR_BAD_ARG;
+  if (out_dtype != DVLP_F32 && out_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
+  if (shard_floats == 0 || (shard_floats & 3) || (arena_offset & 15) || ((uintptr_t)out & 15)) return DVLP_ERR_MISALIGNED;
+  if (arena_offset < dvlp_p2p_control_bytes()) return DVLP_ERR_BAD_ARG;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_p2p_reduce_scatter(peer_arenas, world, rank, arena_offset, shard_floats, out, out_dtype,
+                                (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops
+from . import ops, p2p
 
 
 class CudaBackend:
@@ -32,8 +32,8 @@ class CudaBackend:
                                      lam, focal_equal, impl)
 
     @staticmethod
-    def scores_bwd(state, d_scores):
-        return ops.rw_scores_bwd_raw(state, d_scores)
+    def scores_bwd(state, d_scores, d_s_out=None):
+        return ops.rw_scores_bwd_raw(state, d_scores, d_s_out=d_s_out)
 
     @staticmethod
     def rwa_tail(scores, lam, row_offset, n_total, want_grad):
@@ -120,7 +120,7 @@ class _ShardedRWA(torch.autograd.Function):
     """local_loss of the concatenated batch from row shards (model/loss.py:105-116 on P ranks)."""
 
     @staticmethod
-    def forward(ctx, im, s, im_m, s_m, lam, focal_equal, impl, group, pre=None):
+    def forward(ctx, im, s, im_m, s_m, lam, focal_equal, impl, group, pre=None, xchg=None, ticket=None):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         b = s.shape[0]
         if im.shape[0] != b:
@@ -132,9 +132,13 @@ class _ShardedRWA(torch.autograd.Function):
         scores, state = _BACKEND.scores_fwd(im.detach(), s_all, im_m, s_m_all, lam, focal_equal, impl)
         want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         part, d_scores = _BACKEND.rwa_tail(scores, lam, rank * b, world * b, want)
-        loss = part.clone()
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)   # rows are rank-local: one scalar
+        if xchg is not None:
+            loss = xchg.sum_scalar(part)                            # peer-memory transport (p2p.py)
+        else:
+            loss = part.clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)   # rows are rank-local: one scalar
         ctx.state, ctx.d_scores, ctx.group, ctx.b = state, d_scores, group, b
+        ctx.xchg, ctx.ticket = xchg, ticket
         ctx.dtypes = (im.dtype, s.dtype)
         return loss
 
@@ -142,11 +146,16 @@ class _ShardedRWA(torch.autograd.Function):
     def backward(ctx, g):
         if ctx.d_scores is None:
             raise RuntimeError("sharded RWALoss was evaluated without grad")
-        d_im, d_s_all = _BACKEND.scores_bwd(ctx.state, ctx.d_scores * g)
         # every rank holds a partial gradient for ALL texts: sum and hand each rank its rows
-        d_s = torch.empty((ctx.b,) + tuple(d_s_all.shape[1:]), dtype=d_s_all.dtype, device=d_s_all.device)
-        dist.reduce_scatter_tensor(d_s, d_s_all.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
-        return d_im.to(ctx.dtypes[0]), d_s.to(ctx.dtypes[1]), None, None, None, None, None, None, None
+        if ctx.xchg is not None:
+            ctx.xchg.check(ctx.ticket)                      # the gathered texts of this forward are still in place
+            d_im, _ = _BACKEND.scores_bwd(ctx.state, ctx.d_scores * g, d_s_out=ctx.xchg.reduce_buffer())
+            d_s = ctx.xchg.reduce_scatter(ctx.dtypes[1] if ctx.dtypes[1] == torch.bfloat16 else torch.float32)
+        else:
+            d_im, d_s_all = _BACKEND.scores_bwd(ctx.state, ctx.d_scores * g)
+            d_s = torch.empty((ctx.b,) + tuple(d_s_all.shape[1:]), dtype=d_s_all.dtype, device=d_s_all.device)
+            dist.reduce_scatter_tensor(d_s, d_s_all.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
+        return (d_im.to(ctx.dtypes[0]), d_s.to(ctx.dtypes[1]), None, None, None, None, None, None, None, None, None)
 
 
 class ShardedGlobalLocalLoss(nn.Module):
@@ -161,7 +170,8 @@ class ShardedGlobalLocalLoss(nn.Module):
     """
 
     def __init__(self, temperature=0.05, lambda_softmax=20, focal_type="prob", margin=0,
-                 max_violation=False, use_local=True, use_global=True, coef=1000., group=None, impl="auto"):
+                 max_violation=False, use_local=True, use_global=True, coef=1000., group=None, impl="auto",
+                 transport="auto"):
         super().__init__()
         self.temperature = temperature
         self.lambda_softmax = lambda_softmax
@@ -171,6 +181,11 @@ class ShardedGlobalLocalLoss(nn.Module):
         self.cof_local = coef
         self.group = group
         self.impl = impl
+        if transport not in ("auto", "nccl", "p2p"):
+            raise ValueError("transport must be 'auto', 'nccl' or 'p2p'")
+        self.transport = transport          # "p2p": own kernels over peer memory (p2p.py); "nccl": torch.distributed
+        self._xchg = None
+        self._p2p_failed = False
 
     def global_part(self, text_cls, video_cls, pre=None):
         if pre is None:
@@ -179,9 +194,38 @@ class ShardedGlobalLocalLoss(nn.Module):
         v_all = _GatherRows.apply(video_cls, self.group, pre[1])
         return _BACKEND.norm_softmax(_BACKEND.sim_matrix(t_all, v_all), self.temperature)
 
-    def local_part(self, im, s, im_m, s_m, pre=None):
+    def local_part(self, im, s, im_m, s_m, pre=None, xchg=None, ticket=None):
         return _ShardedRWA.apply(im, s, im_m, s_m, self.lambda_softmax, self.focal_type == "equal",
-                                 self.impl, self.group, pre)
+                                 self.impl, self.group, pre, xchg, ticket)
+
+    def _peer_exchange(self, shards, reduce_shard_shape):
+        """The PeerExchange for these shard shapes, or None when the NCCL transport is to be used.  Collective:
+        every rank takes the same decision (a failure anywhere sends everybody to NCCL)."""
+        if self.transport == "nccl" or self._p2p_failed or dist.get_world_size(self.group) == 1:
+            return None
+        if not p2p.available(shards[0]):
+            if self.transport == "p2p":
+                raise RuntimeError("transport='p2p' needs CUDA tensors and torch symmetric memory")
+            return None
+        specs = [(tuple(t.shape), t.dtype) for t in shards]
+        key = (tuple((tuple(sh), dt) for sh, dt in specs), tuple(reduce_shard_shape))
+        if self._xchg is not None and self._xchg.key == key:
+            return self._xchg
+        ok, err = 1, None
+        try:                         # (re)build the arena: shapes are the same on every rank, so all ranks are here
+            if self._xchg is None:
+                self._xchg = p2p.PeerExchange(self.group, shards[0].device)
+            self._xchg.ensure(specs, reduce_shard_shape)
+        except Exception as e:       # e.g. no peer access between the GPUs of this box
+            ok, err = 0, e
+        flag = torch.tensor([ok], device=shards[0].device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if not int(flag.item()):
+            if self.transport == "p2p":
+                raise RuntimeError(f"peer-memory transport unavailable: {err}")
+            self._p2p_failed, self._xchg = True, None
+            return None
+        return self._xchg
 
     def forward(self, global_pair, local_im, local_s, local_im_m, local_s_l, local_s_m):
         zero = torch.tensor([0.0])
@@ -191,10 +235,16 @@ class ShardedGlobalLocalLoss(nn.Module):
         if not self.use_global:
             l = self.local_part(local_im, local_s, local_im_m, local_s_m)
             return l, zero, l
-        # everything that moves in the forward (text embeddings + masks, both CLS matrices) in ONE grouped all-gather
-        t_all, v_all, s_all, s_m_all = gather_cat_many(
-            [global_pair[0].detach(), global_pair[1].detach(), local_s.detach(),
-             local_s_m.detach().to(torch.float32)], self.group)
+        # everything that moves in the forward (text embeddings + masks, both CLS matrices) in ONE exchange:
+        # a store into the peers' arenas (own kernel, p2p.py) or one grouped NCCL all-gather
+        shards = [global_pair[0].detach(), global_pair[1].detach(), local_s.detach(),
+                  local_s_m.detach().to(torch.float32)]
+        xchg = self._peer_exchange(shards, tuple(local_s.shape))
+        ticket = None
+        if xchg is not None:
+            (t_all, v_all, s_all, s_m_all), ticket = xchg.allgather(shards)
+        else:
+            t_all, v_all, s_all, s_m_all = gather_cat_many(shards, self.group)
         g = self.global_part(*global_pair, pre=(t_all, v_all))
-        l = self.local_part(local_im, local_s, local_im_m, local_s_m, pre=(s_all, s_m_all))
+        l = self.local_part(local_im, local_s, local_im_m, local_s_m, pre=(s_all, s_m_all), xchg=xchg, ticket=ticket)
         return g + l, g, l

@@ -48,19 +48,25 @@ def rw_scores_fwd_raw(im, s, im_mask, s_mask, lam, focal_equal, impl):
     return scores, (im, s, im_mask, s_mask, ws, float(lam), int(focal_equal), dt, impl)
 
 
-def rw_scores_bwd_raw(state, d_scores, out_dtype=torch.float32):
+def rw_scores_bwd_raw(state, d_scores, out_dtype=torch.float32, d_s_out=None):
     """Plain backward: (d_im, d_s) for the state returned by rw_scores_fwd_raw, fp32 unless ``out_dtype`` is
-    bf16 and the tcgen05 path serves the shape (its finalisation kernel then writes bf16 directly)."""
+    bf16 and the tcgen05 path serves the shape (its finalisation kernel then writes bf16 directly).
+    ``d_s_out``: optional preallocated fp32 (Bt, W, d) tensor to receive d_s (e.g. a peer-visible arena region)."""
     im, s, im_mask, s_mask, ws, lam, focal_equal, dt, impl = state
     lib = _lib.load()
     Bv, R, d = im.shape
     Bt, W, _ = s.shape
     d_scores = d_scores.to(torch.float32).contiguous()
     direct = (out_dtype == torch.bfloat16 and impl != _lib.IMPL_GENERIC and lib.dvlp_rw_tcgen05_supported(R, W, d)
-              and os.environ.get("DVLP_TC_BWD", "2") != "0")
+              and os.environ.get("DVLP_TC_BWD", "2") != "0" and d_s_out is None)
     odt = torch.bfloat16 if direct else torch.float32
     d_im = torch.empty(Bv, R, d, dtype=odt, device=im.device)
-    d_s = torch.empty(Bt, W, d, dtype=odt, device=im.device)
+    if d_s_out is not None:
+        if d_s_out.dtype != torch.float32 or tuple(d_s_out.shape) != (Bt, W, d) or not d_s_out.is_contiguous():
+            raise RuntimeError("d_s_out must be a contiguous fp32 (Bt, W, d) tensor")
+        d_s = d_s_out
+    else:
+        d_s = torch.empty(Bt, W, d, dtype=odt, device=im.device)
     with torch.cuda.device(im.device):
         rc = lib.dvlp_rw_scores_bwd(_lib.ptr(im), _lib.ptr(s), _lib.ptr(im_mask), _lib.ptr(s_mask),
                                     Bv, Bt, R, W, d, lam, focal_equal, dt, impl,

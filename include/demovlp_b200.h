@@ -139,6 +139,37 @@ int dvlp_normsoftmax_fwd_bwd(const float* x, int N, int M, float temperature,
 int dvlp_ranks_t2v(const double* sims, int Nq, int Nv, int32_t* ranks, void* stream);
 int dvlp_ranks_v2t(const double* sims, int Nq, int Nv, double* ranks, void* stream);
 
+/*
+ * Peer-memory exchanges of the video-row sharded loss (one process per GPU of one NVLink / NVSwitch box).
+ * They carry what the reference's AllGather_multi pattern (trainer/trainer_dist.py:13-31; all_gather forward,
+ * own-slice backward) moves when the global batch is sharded by video rows: the all-gather of the text side,
+ * the sum of the row-local RWALoss partials (model/loss.py:108-114) and the reduce-scatter of the text gradients.
+ *
+ * Every rank owns an ARENA of the same size and layout whose first dvlp_p2p_control_bytes() bytes are the
+ * library's control block (zero it once, then barrier, before the first call).  `peer_arenas` is a DEVICE array
+ * of `world` pointers: this process's mappings of the arenas of ranks 0..world-1 (peer_arenas[rank] is its own),
+ * e.g. the buffer_ptrs of torch symmetric memory or cudaIpcOpenMemHandle results.  All ranks must issue the same
+ * sequence of these calls.  The calls only enqueue kernels on `stream` (CUDA-graph capturable); flags carry an
+ * epoch kept in the control block.
+ *
+ *   dvlp_p2p_allgather       for t < n_tensors: stores this rank's shard (shards_host[t], shard_bytes_host[t] bytes,
+ *                            multiple of 16) at arena_offsets_host[t] + rank * shard_bytes in EVERY arena and returns
+ *                            (in stream order) once all ranks' shards have landed in this rank's arena.
+ *                            *_host arguments are HOST arrays (n_tensors <= 8).
+ *   dvlp_p2p_sum_scalar      out = sum over ranks of *value, added in rank order (same bits on every rank).
+ *   dvlp_p2p_reduce_scatter  every arena holds, at arena_offset, world * shard_floats fp32 partial sums (completed
+ *                            by earlier work of `stream`); out (shard_floats elements of out_dtype) = sum over ranks
+ *                            of rows [rank * shard_floats, (rank + 1) * shard_floats), added in rank order.
+ * A data region may be overwritten again only after a later exchange of the same call sequence has completed
+ * (the sharded loss alternates allgather -> sum_scalar -> reduce_scatter).
+ */
+size_t dvlp_p2p_control_bytes(void);
+int dvlp_p2p_allgather(void* const* peer_arenas, int world, int rank, int n_tensors, const void* const* shards_host,
+                       const size_t* shard_bytes_host, const size_t* arena_offsets_host, void* stream);
+int dvlp_p2p_sum_scalar(void* const* peer_arenas, int world, int rank, const float* value, float* out, void* stream);
+int dvlp_p2p_reduce_scatter(void* const* peer_arenas, int world, int rank, size_t arena_offset, size_t shard_floats,
+                            void* out, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,55 @@ def test_sharded_loss_two_gpus_matches_single_gpu():
         assert rel_err(o["d_s"], s.grad.float().cpu()[sl]) < 1e-2
         assert rel_err(o["d_gt"], gt.grad.cpu()[sl]) < 1e-4
         assert rel_err(o["d_gv"], gv.grad.cpu()[sl]) < 1e-4
+
+
+def _worker_transport(rank, world, port, out_dir, b):
+    """Same sharded step through both transports: own peer-memory kernels (p2p) and NCCL."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from demovlp_b200 import dist as D, synth
+    full = synth.make_batch(world * b, 80, 32, 256, seed=5)
+    sh = full.rows(rank * b, (rank + 1) * b).to(f"cuda:{rank}")
+    res = {}
+    for transport in ("p2p", "nccl"):
+        mod = D.ShardedGlobalLocalLoss(focal_type="equal", coef=1.0, transport=transport)
+        for it in range(3):      # several steps: the flag epochs of the peer transport advance
+            im = sh.im.to(torch.bfloat16).requires_grad_(True)
+            s = sh.s.to(torch.bfloat16).requires_grad_(True)
+            gt = sh.g_text.clone().requires_grad_(True)
+            gv = sh.g_vid.clone().requires_grad_(True)
+            loss, g, l = mod((gt, gv), im, s, sh.im_mask, sh.s_len, sh.s_mask)
+            loss.backward()
+        torch.cuda.synchronize()
+        res[transport] = dict(loss=loss.detach().cpu(), l=l.detach().cpu(), d_im=im.grad.float().cpu(),
+                              d_s=s.grad.float().cpu(), d_gt=gt.grad.cpu(), d_gv=gv.grad.cpu())
+    torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_peer_memory_transport_matches_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from tests.util import rel_err
+    world, b = 2, 16
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker_transport, args=(world, port, td, b), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(td, f"rank{r}.pt")) for r in range(world)]
+    for o in outs:
+        a, c = o["p2p"], o["nccl"]
+        assert abs(a["loss"].item() - c["loss"].item()) < 1e-6 * max(1, abs(c["loss"].item()))
+        assert torch.equal(a["d_im"], c["d_im"])                    # same kernels, same inputs
+        assert rel_err(a["d_s"], c["d_s"]) < 4e-3                   # one bf16 rounding, sums in a different order
+        assert torch.equal(a["d_gt"], c["d_gt"]) and torch.equal(a["d_gv"], c["d_gv"])
+    # every rank got the same loss bits from the rank-ordered scalar sum
+    assert outs[0]["p2p"]["loss"].item() == outs[1]["p2p"]["loss"].item()
