@@ -62,7 +62,7 @@ void* g_trace_buffer = nullptr;   // set through dvlp_debug_set_trace (tools/tra
 // shapes served by the tcgen05 kernels: d = 256, W = 32 words, R a multiple of 16 in [32, 80]
 bool tc_supported(int R, int W, int d) { return d == 256 && W == 32 && (R == 80 || R == 64 || R == 48 || R == 32); }
 
-Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc) {
+Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc, bool train) {
   Workspace L{};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
@@ -73,10 +73,12 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   L.beta = take(nt_pad * 4);
   L.mterm_v = take(nv * 4);
   L.mterm_t = take(nt_pad * 4);
-  L.vh = take(nv * d * 4);
-  L.th = take(nt * d * 4);
-  L.gv = take(nv * R * 4);
-  L.gt = take(nt * W * 4);
+  // (train == false: forward-only layout -- nothing the backward alone needs is allocated)
+  const bool generic_rows = train || !tc;       // fp32 normalised rows / Gram matrices of the generic kernels
+  L.vh = take(generic_rows ? nv * d * 4 : 0);
+  L.th = take(generic_rows ? nt * d * 4 : 0);
+  L.gv = take(generic_rows ? nv * R * 4 : 0);
+  L.gt = take(generic_rows ? nt * W * 4 : 0);
   bool copy = tc && in_dtype == DVLP_F32;
   L.vb = take(copy ? nv * d * 2 : 0);
   L.tb = take(copy ? nt * d * 2 : 0);
@@ -84,15 +86,15 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   L.gtb = take(tc ? nt_pad * W * 2 : 0);
   L.m2v = take(tc ? nv * 4 : 0);
   L.m2t = take(tc ? nt_pad * 4 : 0);
-  L.dvh = take(nv * d * 4);
-  L.dth = take(nt * d * 4);
-  L.dgv = take(nv * R * 4);
-  L.dgt = take(nt * W * 4);
+  L.dvh = take(train ? nv * d * 4 : 0);
+  L.dth = take(train ? nt * d * 4 : 0);
+  L.dgv = take(train ? nv * R * 4 : 0);
+  L.dgt = take(train ? nt * W * 4 : 0);
   {
     const size_t units = (size_t)Bv * ((Bt + 3) / 4);
-    L.pa = take(tc ? units * R * 128 * 2 : 0);
-    L.rowv = take(tc ? units * 128 * 16 : 0);
-    L.colv = take(tc ? units * 4 * R * 16 : 0);
+    L.pa = take(tc && train ? units * R * 128 * 2 : 0);
+    L.rowv = take(tc && train ? units * 128 * 16 : 0);
+    L.colv = take(tc && train ? units * 4 * R * 16 : 0);
     L.gbd = take(tc ? (size_t)((Bt + 3) / 4) * 128 * 128 * 2 : 0);
   }
   // generic kernels (also the backward fallback of the tcgen05 forward): per-CTA scratch
@@ -187,23 +189,29 @@ int dvlp_profile_read(double* ms, int* counts) {
   return DVLP_OK;
 }
 
-size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl) {
+static size_t workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl, bool train) {
   if (Bv <= 0 || Bt <= 0 || R <= 0 || W <= 0 || d <= 0) return 0;
   bool tc = false;
   if (pick_tc(impl, R, W, d, &tc) != DVLP_OK) return 0;
-  return make_workspace(Bv, Bt, R, W, d, in_dtype, tc).total;
+  return make_workspace(Bv, Bt, R, W, d, in_dtype, tc, train).total;
+}
+size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl) {
+  return workspace_bytes(Bv, Bt, R, W, d, in_dtype, impl, true);
+}
+size_t dvlp_rw_infer_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl) {
+  return workspace_bytes(Bv, Bt, R, W, d, in_dtype, impl, false);
 }
 
-int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
-                       int R, int W, int d, float lambda, int focal_equal, int in_dtype, int impl, float* scores,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+static int scores_fwd(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
+                      int R, int W, int d, float lambda, int focal_equal, int in_dtype, int impl, float* scores,
+                      void* workspace, size_t workspace_bytes, void* stream, bool train) {
   int rc = check_common(im, s, im_mask, s_mask, Bv, Bt, R, W, d, in_dtype);
   if (rc) return rc;
   if (!scores) return DVLP_ERR_NULL_POINTER;
   bool tc = false;
   if ((rc = pick_tc(impl, R, W, d, &tc))) return rc;
   if ((rc = device_ok())) return rc;
-  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc);
+  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc, train);
   if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
   if ((uintptr_t)workspace & 255) return DVLP_ERR_MISALIGNED;
   char* ws = (char*)workspace;
@@ -216,7 +224,7 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
   if (tc) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
-    return run_pair_fwd2(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, true, st);
+    return run_pair_fwd2(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, train, st);
   }
   PairArgs a{};
   a.vh = (const float*)(ws + L.vh); a.th = (const float*)(ws + L.th);
@@ -226,6 +234,20 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
   a.scores = scores;
   a.scratch = (float*)(ws + L.scratch); a.scratch_per_cta = L.scratch_per_cta;
   return run_pair_generic(false, a, L.n_cta, st);
+}
+
+int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
+                       int R, int W, int d, float lambda, int focal_equal, int in_dtype, int impl, float* scores,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  return scores_fwd(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, focal_equal, in_dtype, impl, scores, workspace,
+                    workspace_bytes, stream, true);
+}
+
+int dvlp_rw_scores_infer(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
+                         int R, int W, int d, float lambda, int focal_equal, int in_dtype, int impl, float* scores,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  return scores_fwd(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, focal_equal, in_dtype, impl, scores, workspace,
+                    workspace_bytes, stream, false);
 }
 
 int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,
@@ -239,7 +261,7 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   bool tc = false;
   if ((rc = pick_tc(impl, R, W, d, &tc))) return rc;
   if ((rc = device_ok())) return rc;
-  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc);
+  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc, true);
   if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;

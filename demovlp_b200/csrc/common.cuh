@@ -95,7 +95,7 @@ struct Workspace {
   size_t scratch_per_cta;    // floats
 };
 
-Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc);
+Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc, bool train = true);
 
 // arguments of the generic pair kernels
 struct PairArgs {

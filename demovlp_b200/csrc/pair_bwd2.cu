@@ -69,7 +69,7 @@ struct Lay {
 };
 
 enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE, U_READY, Y_DONE, DGT_STAGED, DG_DONE, P_READY,
-           P_STORED, kNumBars };
+           P_STORED, UD_READY, kNumBars };
 
 // TMEM columns
 constexpr uint32_t cS = 0, cY1 = 96, cY2 = 192, cDGV = 288, cDGT = 384;
@@ -142,7 +142,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     prefetch_tmap(&mapV); prefetch_tmap(&mapT); prefetch_tmap(&mapGV); prefetch_tmap(&mapGBD); prefetch_tmap(&mapP);
     for (int b = 0; b < kNumBars; ++b) {
       uint32_t cnt = 1;
-      if (b == VEC_FREE || b == U_READY || b == P_READY) cnt = NW;
+      if (b == VEC_FREE || b == U_READY || b == P_READY || b == UD_READY) cnt = NW;
       if (b == DGT_STAGED) cnt = 8;
       mbar_init(bar(b), cnt);
     }
@@ -240,7 +240,9 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           tc_commit(bar(Y_DONE));
         }
         __syncwarp();
-        // ---- dGV += UD1^T U1 (K = 128 words),  dGT = UD2 U2^T (K = R regions): UD was written with U
+        // ---- dGV += UD1^T U1 (K = 128 words),  dGT = UD2 U2^T (K = R regions): UD is written under the Y GEMMs
+        mbar_wait(bar(UD_READY), ph);
+        tc_fence_after();
         TR2(1, 1);
         if (elect_one()) {
 #pragma unroll
@@ -362,30 +364,43 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         }
       }
       if (k > 0) mbar_wait(bar(P_STORED), (k - 1) & 1);     // the TMA store of tile k-1 has read the U1 buffer
-      {
-        const float dDA = -0.5f * c1A * kapA;
 #pragma unroll
-        for (int hseg = 0; hseg < 2; ++hseg) {
-          const uint32_t so = hseg ? seg1 : seg0;
-          uint32_t w1[4], w2[4], e1[4], e2[4];
+      for (int hseg = 0; hseg < 2; ++hseg) {
+        const uint32_t so = hseg ? seg1 : seg0;
+        uint32_t w1[4], w2[4];
 #pragma unroll
-          for (int p2 = 0; p2 < 4; ++p2) {
-            const int c = hseg * 8 + p2 * 2;
-            w1[p2] = prmt(ub[c], ub[c + 1], 0x5410);
-            w2[p2] = prmt(ub[c], ub[c + 1], 0x7632);
-            e1[p2] = pack_bf16(bf16_lo(ub[c]) * dDA, bf16_lo(ub[c + 1]) * dDA);
-            e2[p2] = pack_bf16(bf16_hi(ub[c]) * tab[32 + c].z, bf16_hi(ub[c + 1]) * tab[32 + c + 1].z);
-          }
-          st_shared_v4(sbase + L::U1 + so, w1[0], w1[1], w1[2], w1[3]);
-          st_shared_v4(sbase + L::U2 + so, w2[0], w2[1], w2[2], w2[3]);
-          st_shared_v4(sbase + L::UD1 + so, e1[0], e1[1], e1[2], e1[3]);
-          st_shared_v4(sbase + L::UD2 + so, e2[0], e2[1], e2[2], e2[3]);
+        for (int p2 = 0; p2 < 4; ++p2) {
+          const int c = hseg * 8 + p2 * 2;
+          w1[p2] = prmt(ub[c], ub[c + 1], 0x5410);
+          w2[p2] = prmt(ub[c], ub[c + 1], 0x7632);
         }
+        st_shared_v4(sbase + L::U1 + so, w1[0], w1[1], w1[2], w1[3]);
+        st_shared_v4(sbase + L::U2 + so, w2[0], w2[1], w2[2], w2[3]);
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(U_READY));
+      // the u dD operand tiles of the Gram-gradient GEMMs are formed while the Y GEMMs run
+      {
+        const float dDA = -0.5f * c1A * kapA;
+#pragma unroll
+        for (int hseg = 0; hseg < 2; ++hseg) {
+          const uint32_t so = hseg ? seg1 : seg0;
+          uint32_t e1[4], e2[4];
+#pragma unroll
+          for (int p2 = 0; p2 < 4; ++p2) {
+            const int c = hseg * 8 + p2 * 2;
+            e1[p2] = pack_bf16(bf16_lo(ub[c]) * dDA, bf16_lo(ub[c + 1]) * dDA);
+            e2[p2] = pack_bf16(bf16_hi(ub[c]) * tab[32 + c].z, bf16_hi(ub[c + 1]) * tab[32 + c + 1].z);
+          }
+          st_shared_v4(sbase + L::UD1 + so, e1[0], e1[1], e1[2], e1[3]);
+          st_shared_v4(sbase + L::UD2 + so, e2[0], e2[1], e2[2], e2[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(UD_READY));
       TRC(3);
 
       // ---------------- phase 2: dA of both directions, l2-norm backward sums ----------------

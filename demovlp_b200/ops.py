@@ -22,8 +22,9 @@ def _prep_mask(m, like_shape):
     return m.detach().to(torch.float32).contiguous()
 
 
-def rw_scores_fwd_raw(im, s, im_mask, s_mask, lam, focal_equal, impl):
-    """Plain (non-autograd) forward: returns scores and the state the backward needs."""
+def rw_scores_fwd_raw(im, s, im_mask, s_mask, lam, focal_equal, impl, train=True):
+    """Plain (non-autograd) forward: returns scores and the state the backward needs.
+    ``train=False`` takes the forward-only entry point (small workspace, nothing saved; state is None)."""
     _lib.require_cuda(im, s, im_mask, s_mask)
     lib = _lib.load()
     Bv, R, d = im.shape
@@ -35,16 +36,19 @@ def rw_scores_fwd_raw(im, s, im_mask, s_mask, lam, focal_equal, impl):
         im, s = im.float(), s.float()
     dt = _lib.dtype_code(im)
     impl = _lib.impl_code(impl)
-    nbytes = lib.dvlp_rw_workspace_bytes(Bv, Bt, R, W, d, dt, impl)
+    nbytes = (lib.dvlp_rw_workspace_bytes if train else lib.dvlp_rw_infer_workspace_bytes)(Bv, Bt, R, W, d, dt, impl)
     if nbytes == 0:
         raise RuntimeError(f"demovlp_b200: unsupported shape R={R} W={W} d={d} for impl {impl}")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=im.device)
     scores = torch.empty(Bv, Bt, dtype=torch.float32, device=im.device)
     with torch.cuda.device(im.device):
-        rc = lib.dvlp_rw_scores_fwd(_lib.ptr(im), _lib.ptr(s), _lib.ptr(im_mask), _lib.ptr(s_mask),
-                                    Bv, Bt, R, W, d, float(lam), int(focal_equal), dt, impl,
-                                    _lib.ptr(scores), _lib.ptr(ws), nbytes, _lib.stream_ptr())
-    _lib.check(rc, "rw_scores_fwd")
+        fn = lib.dvlp_rw_scores_fwd if train else lib.dvlp_rw_scores_infer
+        rc = fn(_lib.ptr(im), _lib.ptr(s), _lib.ptr(im_mask), _lib.ptr(s_mask),
+                Bv, Bt, R, W, d, float(lam), int(focal_equal), dt, impl,
+                _lib.ptr(scores), _lib.ptr(ws), nbytes, _lib.stream_ptr())
+    _lib.check(rc, "rw_scores_fwd" if train else "rw_scores_infer")
+    if not train:
+        return scores, None
     return scores, (im, s, im_mask, s_mask, ws, float(lam), int(focal_equal), dt, impl)
 
 
@@ -82,9 +86,11 @@ class _RWScores(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, im, s, im_mask, s_mask, lam, focal_equal, impl):
-        scores, state = rw_scores_fwd_raw(im, s, im_mask, s_mask, lam, focal_equal, impl)
-        ctx.save_for_backward(*state[:5])
-        ctx.cfg = state[5:]
+        train = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]      # False under no_grad (validation, retrieval)
+        scores, state = rw_scores_fwd_raw(im, s, im_mask, s_mask, lam, focal_equal, impl, train=train)
+        if train:
+            ctx.save_for_backward(*state[:5])
+            ctx.cfg = state[5:]
         return scores
 
     @staticmethod

@@ -86,6 +86,19 @@ int dvlp_rw_scores_fwd(const void* im, const void* s, const float* im_mask, cons
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Forward only (validation / retrieval: RWALoss.get_sim under no_grad, get_sim_by_segment,
+ * model/loss.py:64-103, trainer/trainer_dist.py:369-385): same arguments and scores as
+ * dvlp_rw_scores_fwd, but nothing is kept for a backward -- the workspace
+ * (dvlp_rw_infer_workspace_bytes) holds the per-item prologue only, so a 1000 x 1000 evaluation
+ * needs megabytes instead of gigabytes and the kernel writes nothing but the scores.
+ */
+size_t dvlp_rw_infer_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl);
+int dvlp_rw_scores_infer(const void* im, const void* s, const float* im_mask, const float* s_mask,
+                         int Bv, int Bt, int R, int W, int d, float lambda, int focal_equal,
+                         int in_dtype, int impl, float* scores,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Backward of dvlp_rw_scores_fwd (what autograd does through model/loss.py:209-330):
  * given d_scores (Bv, Bt) fp32 produces d_im (Bv, R, d) and d_s (Bt, W, d) in `out_dtype`
  * (both overwritten; DVLP_F32 always, DVLP_BF16 on the tcgen05 path, else DVLP_ERR_BAD_DTYPE).
