@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(256) k_grad_finalize_tile(const Tin* __restric
 //   d_x_r = D_r - inv_r^2 (x_r . D_r) x_r                       (the l2norm backward, model/loss.py:333-338)
 // Warp w owns rows 16w..16w+15 and all 256 columns (128 accumulator registers per thread).
 constexpr int kFinLdX = (256 + 8) * 2;      // bytes
-template <bool OUT_BF16>
-__global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ t,
+template <bool OUT_BF16, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 320 ? 2 : 1) k_finalize_item(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ t,
                                                        const float* __restrict__ alpha, const float* __restrict__ beta,
                                                        const float* __restrict__ dvh, const float* __restrict__ dth,
                                                        const float* __restrict__ dgv, const float* __restrict__ dgt,
@@ -164,59 +164,73 @@ __global__ void __launch_bounds__(256) k_finalize_item(const __nv_bfloat16* __re
     *reinterpret_cast<__nv_bfloat162*>(as + r * ldA + c * 2) = __floats2bfloat162_rn(g.x * sr * s_inv[c], g.y * sr * s_inv[c + 1]);
   }
   __syncthreads();
-  if (warp * 16 >= L) return;
-  const int row0 = warp * 16, g = lane >> 2, tq = lane & 3;
-  float acc[32][4];
-#pragma unroll
-  for (int n = 0; n < 32; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-  for (int k0 = 0; k0 < L; k0 += 16) {
-    uint32_t a[4];
-    mm::load_a(ab, ldA, row0, k0, lane, a);
-#pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) {
-      uint32_t b[4];
-      mm::load_b_kn(xb, kFinLdX, k0, n2 * 16, lane, b);
-      mm::mma_16816(acc[2 * n2], a[0], a[1], a[2], a[3], b[0], b[1]);
-      mm::mma_16816(acc[2 * n2 + 1], a[0], a[1], a[2], a[3], b[2], b[3]);
-    }
-  }
-  // add the prescaled S-path gradient; row dots with the raw row
-  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+  // warp = (16-row block, 128-column half): 64 accumulator registers per thread, so that two CTAs fit an SM and all
+  // items of a config-2 step are resident at once.  The launch provides one warp per task (2 L / 16 warps).
+  __shared__ float s_dot[2][128];
+  const int nrb = L >> 4;
+  const int g = lane >> 2, tq = lane & 3;
+  float acc[16][4];
   float dot_lo = 0.f, dot_hi = 0.f;
+  const bool active = warp < 2 * nrb;
+  const int row0 = (warp >> 1) * 16, ch = warp & 1, col0 = ch * 128;
+  if (active) {
 #pragma unroll
-  for (int n = 0; n < 32; ++n) {
-    const int c = n * 8 + tq * 2;
-    const float2 d_lo = *reinterpret_cast<const float2*>(dX + (size_t)r_lo * 256 + c);
-    const float2 d_hi = *reinterpret_cast<const float2*>(dX + (size_t)r_hi * 256 + c);
-    acc[n][0] += d_lo.x; acc[n][1] += d_lo.y; acc[n][2] += d_hi.x; acc[n][3] += d_hi.y;
-    const uint32_t x_lo = *reinterpret_cast<const uint32_t*>(xs + r_lo * kFinLdX + c * 2);
-    const uint32_t x_hi = *reinterpret_cast<const uint32_t*>(xs + r_hi * kFinLdX + c * 2);
-    dot_lo = fmaf(__uint_as_float(x_lo << 16), acc[n][0], dot_lo);
-    dot_lo = fmaf(__uint_as_float(x_lo & 0xffff0000u), acc[n][1], dot_lo);
-    dot_hi = fmaf(__uint_as_float(x_hi << 16), acc[n][2], dot_hi);
-    dot_hi = fmaf(__uint_as_float(x_hi & 0xffff0000u), acc[n][3], dot_hi);
+    for (int n = 0; n < 16; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    for (int k0 = 0; k0 < L; k0 += 16) {
+      uint32_t a[4];
+      mm::load_a(ab, ldA, row0, k0, lane, a);
+#pragma unroll
+      for (int n2 = 0; n2 < 8; ++n2) {
+        uint32_t b[4];
+        mm::load_b_kn(xb, kFinLdX, k0, col0 + n2 * 16, lane, b);
+        mm::mma_16816(acc[2 * n2], a[0], a[1], a[2], a[3], b[0], b[1]);
+        mm::mma_16816(acc[2 * n2 + 1], a[0], a[1], a[2], a[3], b[2], b[3]);
+      }
+    }
+    // add the prescaled S-path gradient; partial row dots with the raw row
+    const int r_lo = row0 + g, r_hi = row0 + g + 8;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      const int c = col0 + n * 8 + tq * 2;
+      const float2 d_lo = *reinterpret_cast<const float2*>(dX + (size_t)r_lo * 256 + c);
+      const float2 d_hi = *reinterpret_cast<const float2*>(dX + (size_t)r_hi * 256 + c);
+      acc[n][0] += d_lo.x; acc[n][1] += d_lo.y; acc[n][2] += d_hi.x; acc[n][3] += d_hi.y;
+      const uint32_t x_lo = *reinterpret_cast<const uint32_t*>(xs + r_lo * kFinLdX + c * 2);
+      const uint32_t x_hi = *reinterpret_cast<const uint32_t*>(xs + r_hi * kFinLdX + c * 2);
+      dot_lo = fmaf(__uint_as_float(x_lo << 16), acc[n][0], dot_lo);
+      dot_lo = fmaf(__uint_as_float(x_lo & 0xffff0000u), acc[n][1], dot_lo);
+      dot_hi = fmaf(__uint_as_float(x_hi << 16), acc[n][2], dot_hi);
+      dot_hi = fmaf(__uint_as_float(x_hi & 0xffff0000u), acc[n][3], dot_hi);
+    }
+    dot_lo += __shfl_xor_sync(0xffffffffu, dot_lo, 1); dot_lo += __shfl_xor_sync(0xffffffffu, dot_lo, 2);
+    dot_hi += __shfl_xor_sync(0xffffffffu, dot_hi, 1); dot_hi += __shfl_xor_sync(0xffffffffu, dot_hi, 2);
+    if (tq == 0) { s_dot[ch][r_lo] = dot_lo; s_dot[ch][r_hi] = dot_hi; }
   }
-  dot_lo += __shfl_xor_sync(0xffffffffu, dot_lo, 1); dot_lo += __shfl_xor_sync(0xffffffffu, dot_lo, 2);
-  dot_hi += __shfl_xor_sync(0xffffffffu, dot_hi, 1); dot_hi += __shfl_xor_sync(0xffffffffu, dot_hi, 2);
-  const float k_lo = s_inv[r_lo] * s_inv[r_lo] * dot_lo, k_hi = s_inv[r_hi] * s_inv[r_hi] * dot_hi;
+  __syncthreads();
+  if (active) {
+    const int r_lo = row0 + g, r_hi = row0 + g + 8;
+    const float k_lo = s_inv[r_lo] * s_inv[r_lo] * (s_dot[0][r_lo] + s_dot[1][r_lo]);
+    const float k_hi = s_inv[r_hi] * s_inv[r_hi] * (s_dot[0][r_hi] + s_dot[1][r_hi]);
 #pragma unroll
-  for (int n = 0; n < 32; ++n) {
-    const int c = n * 8 + tq * 2;
-    const uint32_t x_lo = *reinterpret_cast<const uint32_t*>(xs + r_lo * kFinLdX + c * 2);
-    const uint32_t x_hi = *reinterpret_cast<const uint32_t*>(xs + r_hi * kFinLdX + c * 2);
-    float2 o_lo, o_hi;
-    o_lo.x = fmaf(-k_lo, __uint_as_float(x_lo << 16), acc[n][0]);
-    o_lo.y = fmaf(-k_lo, __uint_as_float(x_lo & 0xffff0000u), acc[n][1]);
-    o_hi.x = fmaf(-k_hi, __uint_as_float(x_hi << 16), acc[n][2]);
-    o_hi.y = fmaf(-k_hi, __uint_as_float(x_hi & 0xffff0000u), acc[n][3]);
-    if (OUT_BF16) {
-      __nv_bfloat16* ob = (__nv_bfloat16*)out_base + out_off;
-      *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)r_lo * 256 + c) = __floats2bfloat162_rn(o_lo.x, o_lo.y);
-      *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)r_hi * 256 + c) = __floats2bfloat162_rn(o_hi.x, o_hi.y);
-    } else {
-      float* of = (float*)out_base + out_off;
-      *reinterpret_cast<float2*>(of + (size_t)r_lo * 256 + c) = o_lo;
-      *reinterpret_cast<float2*>(of + (size_t)r_hi * 256 + c) = o_hi;
+    for (int n = 0; n < 16; ++n) {
+      const int c = col0 + n * 8 + tq * 2;
+      const float a0 = acc[n][0], a1 = acc[n][1], a2 = acc[n][2], a3 = acc[n][3];
+      const uint32_t x_lo = *reinterpret_cast<const uint32_t*>(xs + r_lo * kFinLdX + c * 2);
+      const uint32_t x_hi = *reinterpret_cast<const uint32_t*>(xs + r_hi * kFinLdX + c * 2);
+      float2 o_lo, o_hi;
+      o_lo.x = fmaf(-k_lo, __uint_as_float(x_lo << 16), a0);
+      o_lo.y = fmaf(-k_lo, __uint_as_float(x_lo & 0xffff0000u), a1);
+      o_hi.x = fmaf(-k_hi, __uint_as_float(x_hi << 16), a2);
+      o_hi.y = fmaf(-k_hi, __uint_as_float(x_hi & 0xffff0000u), a3);
+      if (OUT_BF16) {
+        __nv_bfloat16* ob = (__nv_bfloat16*)out_base + out_off;
+        *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)r_lo * 256 + c) = __floats2bfloat162_rn(o_lo.x, o_lo.y);
+        *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)r_hi * 256 + c) = __floats2bfloat162_rn(o_hi.x, o_hi.y);
+      } else {
+        float* of = (float*)out_base + out_off;
+        *reinterpret_cast<float2*>(of + (size_t)r_lo * 256 + c) = o_lo;
+        *reinterpret_cast<float2*>(of + (size_t)r_hi * 256 + c) = o_hi;
+      }
     }
   }
 }
@@ -227,20 +241,21 @@ int run_grad_finalize_tc(const void* v, const void* t, const float* alpha, const
                          void* d_im, void* d_s, int out_dtype, cudaStream_t st) {
   const int Lmax = R > W ? R : W;
   const size_t smem = (size_t)Lmax * kFinLdX + (size_t)Lmax * (Lmax + 8) * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DVLP_CUDA_OK(cudaFuncSetAttribute(k_finalize_item<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      128 * kFinLdX + 128 * 136 * 2));
-    DVLP_CUDA_OK(cudaFuncSetAttribute(k_finalize_item<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      128 * kFinLdX + 128 * 136 * 2));
-    attr_set = true;
-  }
-  if (out_dtype == DVLP_BF16)
-    k_finalize_item<true><<<Bv + Bt, 256, smem, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)t, alpha, beta, dvh,
-                                                      dth, dgv, dgt, Bv, R, W, dgt_swz, d_im, d_s);
+  const int threads = 64 * (Lmax / 16);        // one warp per (16-row block, 128-column half)
+  auto launch = [&](auto kern) -> int {
+    // two CTAs per SM need the large shared-memory carveout (the default one fits a single 57 KB block)
+    DVLP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kFinLdX + 128 * 136 * 2));
+    DVLP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<Bv + Bt, threads, smem, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)t, alpha, beta, dvh, dth, dgv, dgt,
+                                         Bv, R, W, dgt_swz, d_im, d_s);
+    return DVLP_OK;
+  };
+  int rc;
+  if (threads <= 320)
+    rc = out_dtype == DVLP_BF16 ? launch(k_finalize_item<true, 320>) : launch(k_finalize_item<false, 320>);
   else
-    k_finalize_item<false><<<Bv + Bt, 256, smem, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)t, alpha, beta, dvh,
-                                                       dth, dgv, dgt, Bv, R, W, dgt_swz, d_im, d_s);
+    rc = out_dtype == DVLP_BF16 ? launch(k_finalize_item<true, 512>) : launch(k_finalize_item<false, 512>);
+  if (rc) return rc;
   DVLP_LAUNCH_OK();
   return DVLP_OK;
 }
