@@ -345,3 +345,50 @@ def test_graphed_step_matches_eager():
     t2 = {**t, "im": b2.im.to(torch.bfloat16), "s": b2.s.to(torch.bfloat16)}
     want = fn(t2)
     assert abs(float(l2[2]) - float(want[2])) < 1e-4
+
+
+def test_forward_only_entry_point_matches_training_forward():
+    """dvlp_rw_scores_infer (no_grad / retrieval) gives the training forward's scores bit for bit, from a workspace
+    that holds the prologue only."""
+    lib = _lib.load()
+    for (Bv, Bt, R, W) in ((16, 24, 80, 32), (7, 9, 30, 99)):
+        b = dev(synth.make_batch(Bv, R, W, 256, seed=21, Bt=Bt))
+        im, s = b.im.to(torch.bfloat16), b.s.to(torch.bfloat16)
+        train, state = ops.rw_scores_fwd_raw(im, s, b.im_mask, b.s_mask, 20.0, 1, "auto", train=True)
+        infer, none = ops.rw_scores_fwd_raw(im, s, b.im_mask, b.s_mask, 20.0, 1, "auto", train=False)
+        assert none is None and state is not None
+        assert torch.equal(train, infer)
+        big = lib.dvlp_rw_workspace_bytes(Bv, Bt, R, W, 256, _lib.BF16, 0)
+        small = lib.dvlp_rw_infer_workspace_bytes(Bv, Bt, R, W, 256, _lib.BF16, 0)
+        assert 0 < small < big
+        # the module takes it under no_grad and for inputs that need no gradient
+        mod = L.RWALoss(20, "equal")
+        with torch.no_grad():
+            assert torch.equal(mod.get_sim(im, s, b.im_mask, None, b.s_mask), train)
+        assert torch.equal(mod.get_sim(im, s, b.im_mask, None, b.s_mask), train)
+
+
+def test_loss_tail_kernels_shape_boundaries():
+    """Cluster tail kernels: RWALoss rows wider than the 1024-score register path, NormSoftmax on both sides of the
+    single-launch limit (256), non-square blocks."""
+    from tests import emul
+    gen = torch.Generator().manual_seed(11)
+    for (rows, cols, off) in ((40, 1500, 100), (3, 1025, 0), (300, 300, 0), (1, 1, 0)):
+        sc = torch.randn(rows, cols, generator=gen) * 0.3
+        want_l, want_g = emul.rwa_loss_fwd_bwd(sc, 20.0, off, cols)
+        got_l, got_g = ops.rwa_tail_raw(sc.cuda(), 20.0, off, cols)
+        assert abs(got_l.item() - float(want_l)) < 1e-4 * max(1, abs(float(want_l)))
+        assert rel_err(got_g.cpu(), want_g) < 1e-4
+    for (n, m) in ((256, 256), (257, 256), (256, 257), (1, 1), (3, 200)):
+        x = (torch.rand(n, m, generator=gen) * 2 - 1).requires_grad_(True)
+        want = O.norm_softmax_loss(x, 0.05)
+        want.backward()
+        y = x.detach().cuda().requires_grad_(True)
+        got = L.NormSoftmaxLoss(0.05)(y)
+        got.backward()
+        assert abs(got.item() - want.item()) < 1e-4 * max(1, abs(want.item()))
+        assert rel_err(y.grad.cpu(), x.grad) < 1e-4
+    # deterministic: the cluster reductions add in a fixed order
+    sc = (torch.randn(128, 1024, generator=gen) * 0.3).cuda()
+    a = ops.rwa_tail_raw(sc, 20.0, 0, 1024)[0].item()
+    assert all(ops.rwa_tail_raw(sc, 20.0, 0, 1024)[0].item() == a for _ in range(5))
