@@ -44,6 +44,22 @@ def test_error_strings_and_validation_without_gpu():
     assert lib.dvlp_ranks_t2v(z, 4, 4, z, z) == -3
     assert lib.dvlp_ranks_t2v(one, 2, 4, one, z) == -1
     assert lib.dvlp_normsoftmax_fwd_bwd(one, 4, 4, 0.0, one, z, one, z) == -8
+    assert lib.dvlp_rw_scores_infer(z, z, z, z, 1, 1, 1, 1, 8, 20.0, 1, 0, 1, z, z, 0, z) == -3
+    small = lib.dvlp_rw_infer_workspace_bytes(128, 128, 80, 32, 256, _lib.BF16, _lib.IMPL_TCGEN05)
+    assert 0 < small < lib.dvlp_rw_workspace_bytes(128, 128, 80, 32, 256, _lib.BF16, _lib.IMPL_TCGEN05)
+    # peer-memory exchanges: argument checks come before any device work
+    ctrl = lib.dvlp_p2p_control_bytes()
+    assert ctrl >= 1024 and ctrl % 256 == 0
+    src = (C.c_void_p * 1)(256)
+    nb = (C.c_size_t * 1)(64)
+    off = (C.c_size_t * 1)(ctrl)
+    assert lib.dvlp_p2p_allgather(z, 2, 0, 1, src, nb, off, z) == -3
+    assert lib.dvlp_p2p_allgather(one, 2, 2, 1, src, nb, off, z) == -8            # rank outside the world
+    assert lib.dvlp_p2p_allgather(one, 2, 0, 1, src, (C.c_size_t * 1)(40), off, z) == -4   # not a multiple of 16 bytes
+    assert lib.dvlp_p2p_allgather(one, 2, 0, 1, src, nb, (C.c_size_t * 1)(0), z) == -8     # inside the control block
+    assert lib.dvlp_p2p_sum_scalar(one, 65, 0, one, one, z) == -8
+    assert lib.dvlp_p2p_reduce_scatter(one, 2, 0, ctrl, 6, one, _lib.F32, z) == -4          # shard not a multiple of 4 floats
+    assert lib.dvlp_p2p_reduce_scatter(one, 2, 0, ctrl, 8, one, 9, z) == -2
     if not torch.cuda.is_available():
         # valid arguments, no device: the library says so instead of computing anything
         assert lib.dvlp_rwa_loss_fwd_bwd(one, 4, 4, 0, 4, 20.0, one, z, z) == -7
