@@ -248,3 +248,72 @@ class ShardedGlobalLocalLoss(nn.Module):
         g = self.global_part(*global_pair, pre=(t_all, v_all))
         l = self.local_part(local_im, local_s, local_im_m, local_s_m, pre=(s_all, s_m_all), xchg=xchg, ticket=ticket)
         return g + l, g, l
+
+
+class ValidationFeed:
+    """Device-resident replacement for the reference's validation bookkeeping (trainer/trainer_dist.py:218-391).
+
+    The reference all-gathers seven tensors per validation batch, moves every gathered tensor to the CPU, concatenates
+    there, computes ``sim_matrix`` on CPU tensors and re-uploads 8 x 8 tiles for the local scores.  Here each rank keeps
+    its own batch outputs on the GPU (``add``), ``finish`` moves them ONCE (one grouped all-gather per tensor over all
+    batches) and restores the reference's row order -- batch-major, rank-major inside a batch, exactly what its per-batch
+    ``torch.cat(all_gather(...))`` + final ``torch.cat`` produce --, and ``similarity`` feeds the fused forward-only
+    kernels and the rank kernels directly.  Single process (no process group): ``finish`` is a plain concatenation.
+    """
+
+    KEYS = ("global_text", "global_object", "local_text", "local_object", "object_mask", "text_mask", "text_length")
+
+    def __init__(self, group=None):
+        self.group = group
+        self.batches = []
+        self.data = None
+
+    def add(self, global_text, global_object, local_text, local_object, object_mask, attention_mask_tail, text_length):
+        """One validation batch of THIS rank (model outputs, trainer_dist.py:270-321).  ``attention_mask_tail`` is the
+        tokenizer's 0/1 mask without the CLS column (``data['text']['attention_mask'][:, 1:]``, :262-267); it becomes
+        the additive mask ``(m - 1) * 100`` of :323."""
+        text_mask = (attention_mask_tail.to(torch.float32) - 1.0) * 100.0
+        self.batches.append(tuple(t.detach() for t in (global_text, global_object, local_text, local_object,
+                                                       object_mask, text_mask, text_length)))
+
+    def finish(self):
+        """Gather all batches of all ranks; returns the dict of concatenated tensors in the reference's order."""
+        if not self.batches:
+            raise RuntimeError("ValidationFeed.finish: no batches were added")
+        mine = [torch.cat([b[k] for b in self.batches]).contiguous() for k in range(len(self.KEYS))]
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if not multi:
+            self.data = dict(zip(self.KEYS, mine))
+            return self.data
+        world = dist.get_world_size(self.group)
+        sizes = [b[0].shape[0] for b in self.batches]             # rows per batch (the same on every rank, like the
+        gathered = gather_cat_many(mine, self.group)              # reference's equal-shape all_gather requires)
+        n_local = sum(sizes)
+        # gathered rows are [rank][batch][row]; the reference order is [batch][rank][row]
+        idx, start = [], 0
+        for n in sizes:
+            for r in range(world):
+                idx.append(torch.arange(r * n_local + start, r * n_local + start + n))
+            start += n
+        perm = torch.cat(idx).to(gathered[0].device)
+        self.data = {k: g.index_select(0, perm) for k, g in zip(self.KEYS, gathered)}
+        return self.data
+
+    def similarity(self, loss_module, use_local=True, rows_per_launch=256):
+        """float64 numpy matrix the reference hands to its metrics (:369-385): ``sim_matrix(text, object)`` plus, when
+        ``use_local``, ``local_loss.get_sim_by_segment(...)`` (video rows x text columns -- the reference adds the two
+        orientations as they are, which is only meaningful for one caption per video; kept)."""
+        from . import loss as L
+        d = self.data if self.data is not None else self.finish()
+        sims = L.sim_matrix(d["global_text"], d["global_object"]).detach().to(torch.float64)
+        if use_local:
+            local = loss_module.local_loss
+            n_img = d["local_object"].shape[0]
+            if sims.shape != (d["local_text"].shape[0], n_img) or sims.shape[0] != sims.shape[1]:
+                raise RuntimeError("global (text x video) and local (video x text) matrices only add up when square")
+            with torch.no_grad():
+                for v0 in range(0, n_img, rows_per_launch):
+                    v1 = min(v0 + rows_per_launch, n_img)
+                    sims[v0:v1] += local.get_sim(d["local_object"][v0:v1], d["local_text"], d["object_mask"][v0:v1],
+                                                 d["text_length"], d["text_mask"]).to(torch.float64)
+        return sims.cpu().numpy()

@@ -73,8 +73,16 @@ def _worker(rank, world, port, out_dir):
     x = (torch.arange(b * 3, dtype=torch.float32).view(b, 3) + 100 * rank).requires_grad_(True)
     y = D.AllGather_multi.apply(x, 1, A)
     (y * torch.arange(y.numel(), dtype=torch.float32).view_as(y)).sum().backward()
+    # validation feed: two batches per rank; rows carry (batch, rank, row) tags
+    feed = D.ValidationFeed()
+    for bi, n in enumerate((3, 2)):
+        tag = lambda w: (torch.arange(n, dtype=torch.float32)[:, None] + 10 * rank + 100 * bi).repeat(1, w)
+        feed.add(tag(4), tag(4) + 0.5, tag(6).view(n, 3, 2), tag(8).view(n, 4, 2), tag(4), torch.ones(n, 3), tag(1)[:, 0])
+    val = feed.finish()
     torch.save(dict(loss=loss.detach(), g=g.detach(), l=l.detach(), d_im=im.grad, d_s=s.grad,
-                    d_gt=gt.grad, d_gv=gv.grad, gathered=y.detach(), x_grad=x.grad),
+                    d_gt=gt.grad, d_gv=gv.grad, gathered=y.detach(), x_grad=x.grad,
+                    val_rows=val["global_text"][:, 0].clone(), val_obj=val["local_object"][:, 0, 0].clone(),
+                    val_len=val["text_length"].clone(), val_mask=val["text_mask"].clone()),
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -115,3 +123,8 @@ def test_sharded_loss_equals_oracle_on_concatenated_batch():
         assert torch.equal(o["gathered"], want)
         w = torch.arange(want.numel(), dtype=torch.float32).view_as(want)
         assert torch.equal(o["x_grad"], w[r * b:(r + 1) * b])
+        # ValidationFeed: the reference's order is batch-major, rank-major inside a batch (trainer_dist.py:252-333)
+        order = torch.tensor([100 * bi + 10 * k + i for bi, n in enumerate((3, 2)) for k in range(world) for i in range(n)],
+                             dtype=torch.float32)
+        assert torch.equal(o["val_rows"], order) and torch.equal(o["val_obj"], order) and torch.equal(o["val_len"], order)
+        assert torch.equal(o["val_mask"], torch.zeros(10, 3))          # (1 - 1) * 100

@@ -392,3 +392,22 @@ def test_loss_tail_kernels_shape_boundaries():
     sc = (torch.randn(128, 1024, generator=gen) * 0.3).cuda()
     a = ops.rwa_tail_raw(sc, 20.0, 0, 1024)[0].item()
     assert all(ops.rwa_tail_raw(sc, 20.0, 0, 1024)[0].item() == a for _ in range(5))
+
+
+def test_validation_feed_matches_segmented_eval():
+    """ValidationFeed (device-resident gather + similarity) reproduces what the trainer builds with
+    sim_matrix + get_sim_by_segment on CPU tensors (trainer/trainer_dist.py:358-385)."""
+    from demovlp_b200 import dist as D
+    b = synth.make_batch(40, 80, 32, 256, seed=31)
+    mod = L.GlobalLocalLoss(focal_type="equal")
+    feed = D.ValidationFeed()
+    att = (b.s_mask == 0).to(torch.int64)                  # the tokenizer's 0/1 mask the trainer starts from
+    for lo, hi in ((0, 24), (24, 40)):
+        r = b.rows(lo, hi).to("cuda")
+        feed.add(r.g_text, r.g_vid, r.s.to(torch.bfloat16), r.im.to(torch.bfloat16), r.im_mask, att[lo:hi].cuda(), r.s_len)
+    got = feed.similarity(mod)
+    want = L.sim_matrix(b.g_text.cuda(), b.g_vid.cuda()).double().cpu().numpy() + mod.local_loss.get_sim_by_segment(
+        b.im.to(torch.bfloat16), b.s.to(torch.bfloat16), b.im_mask, b.s_len, b.s_mask, device="cuda")
+    assert got.dtype == np.float64 and got.shape == (40, 40)
+    assert np.array_equal(got, want)
+    assert M.t2v_metrics(got) == M.t2v_metrics(want)
