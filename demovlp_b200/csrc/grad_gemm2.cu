@@ -14,6 +14,8 @@
 // owns them), MODE_T adds its split's partial sums with red.global (a few MB in total).
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -25,34 +27,41 @@ constexpr int kD = 256, kRows = 128, kThreads = 192;
 constexpr int kTileBytes = 16384, kCh32 = 4096;
 enum { MODE_V = 0, MODE_T = 1 };
 
-template <int R, int MODE>
+template <int R, int MODE, int NP>
 struct Lay {
   static constexpr int NC = R / 16;                                   // 16-column chunks of the P tile
   static constexpr int CH = R * 128;                                  // one 64-column chunk of an R-row tile
-  static constexpr int kStages = MODE == MODE_V ? 2 : 3;
-  static constexpr int P = 0, X = NC * kCh32;
+  static constexpr int kStages = NP == 2 ? 2 : (MODE == MODE_V ? 2 : 3);
+  static constexpr int PBYTES = NC * kCh32;
+  static constexpr int P = 0, X = NP * PBYTES;                        // NP P tiles share one X operand
   static constexpr int XBYTES = MODE == MODE_V ? 4 * kTileBytes : 4 * CH;
-  static constexpr int STAGE = NC * kCh32 + XBYTES;
+  static constexpr int STAGE = NP * PBYTES + XBYTES;
   static constexpr int BARS = kStages * STAGE;
   static constexpr int TMEMPTR = BARS + 8 * 8;
   static constexpr int kAlloc = TMEMPTR + 16;
+  static_assert(STAGE % 1024 == 0 && X % 1024 == 0, "128-byte-swizzle tiles need 1 KB alignment");
   static_assert(kAlloc <= 232448, "shared memory budget");
 };
 
 struct Args {
-  int Bv, Bt, tiles_per_video, videos_per_split;
-  long long text_rows;     // Bt * W: valid rows of dT'
-  float* out;              // MODE_V: dV' (Bv, R, d), overwritten;  MODE_T: dT' (Bt*W, d), accumulated
+  int Bv, Bt, tiles_per_video;
+  int n_groups, steps_per_split;  // MODE_V: video groups x text-tile splits;  MODE_T: text-tile groups x video splits
+  int accumulate;                 // 1: red.global.add into `out` (zeroed by the caller), 0: plain stores (one split)
+  long long text_rows;            // Bt * W: valid rows of dT'
+  float* out;                     // MODE_V: dV' (Bv, R, d);  MODE_T: dT' (Bt*W, d)
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int R, int MODE>
+// NP = 1: one accumulator per CTA.  NP = 2 (long K loops, i.e. many texts): the CTA keeps TWO accumulators (all of
+// TMEM) that share the streamed operand -- per step T_jt once + P[2p,jt], P[2p+1,jt] (MODE_V) or V_i once + P[i,2p],
+// P[i,2p+1] (MODE_T): 92 KB instead of 144 KB of L2 -> shared-memory loads per unit over both modes.
+template <int R, int MODE, int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapX, Args a) {
-  using L = Lay<R, MODE>;
+  using L = Lay<R, MODE, NP>;
   constexpr int kStages = L::kStages, NC = L::NC;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
@@ -63,17 +72,13 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
   const uint32_t done = sbase + L::BARS + 8 * (2 * kStages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // this CTA's K loop
-  int i0, n_steps, jt = 0;
-  if (MODE == MODE_V) {
-    i0 = blockIdx.x;                       // video
-    n_steps = a.tiles_per_video;
-  } else {
-    jt = blockIdx.x % a.tiles_per_video;
-    const int z = blockIdx.x / a.tiles_per_video;
-    i0 = z * a.videos_per_split;
-    n_steps = min(a.videos_per_split, a.Bv - i0);
-  }
+  // this CTA's group of NP videos (MODE_V) / text tiles (MODE_T) and its K range
+  const int pr = blockIdx.x % a.n_groups, z = blockIdx.x / a.n_groups;
+  const int k_total = MODE == MODE_V ? a.tiles_per_video : a.Bv;
+  const int k0 = z * a.steps_per_split;
+  const int n_steps = max(0, min(a.steps_per_split, k_total - k0));
+  const int m0 = NP * pr;
+  const int n_mem = min(NP, (MODE == MODE_V ? a.Bv : a.tiles_per_video) - m0);    // members of this group (1 or 2)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapP); prefetch_tmap(&mapX);
@@ -81,7 +86,7 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(sbase + L::TMEMPTR, 256);
+    tmem_alloc(sbase + L::TMEMPTR, 256 * NP);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -95,14 +100,18 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
         const int s = k % kStages, it = k / kStages;
         if (it > 0) mbar_wait(empty(s), (it - 1) & 1);
         const uint32_t st = sbase + s * L::STAGE;
-        const long long unit = MODE == MODE_V ? (long long)i0 * a.tiles_per_video + k
-                                              : (long long)(i0 + k) * a.tiles_per_video + jt;
-        mbar_arrive_expect_tx(full(s), L::STAGE);
-        for (int c = 0; c < NC; ++c) tma_load_2d(st + L::P + c * kCh32, &mapP, c * 16, (int)(unit * kRows), full(s));
+        const int kk = k0 + k;                            // text tile (MODE_V) / video (MODE_T) of this step
+        mbar_arrive_expect_tx(full(s), L::XBYTES + n_mem * L::PBYTES);
+        for (int h = 0; h < n_mem; ++h) {
+          const long long unit = MODE == MODE_V ? (long long)(m0 + h) * a.tiles_per_video + kk
+                                                : (long long)kk * a.tiles_per_video + (m0 + h);
+          for (int c = 0; c < NC; ++c)
+            tma_load_2d(st + L::P + h * L::PBYTES + c * kCh32, &mapP, c * 16, (int)(unit * kRows), full(s));
+        }
         if (MODE == MODE_V) {
-          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * kTileBytes, &mapX, c * 64, k * kRows, full(s));
+          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * kTileBytes, &mapX, c * 64, kk * kRows, full(s));
         } else {
-          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * L::CH, &mapX, c * 64, (i0 + k) * R, full(s));
+          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * L::CH, &mapX, c * 64, kk * R, full(s));
         }
       }
     }
@@ -117,21 +126,25 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
       tc_fence_after();
       if (elect_one()) {
         const uint32_t st = sbase + s * L::STAGE;
-        if (MODE == MODE_V) {
-          // K = 128 words: P rows are the K rows of an MN-major operand whose M (regions) chunks are 4 KB apart;
-          // M = 128 reads past the R valid regions (into the X tile): those accumulator lanes are never stored
-          const uint32_t loX = desc_lo(st + L::X, kTileBytes);
-          const uint32_t loP = desc_lo(st + L::P, kCh32);
+        for (int h = 0; h < n_mem; ++h) {
+          const uint32_t acc = tmem + h * 256;
+          const uint32_t pb = st + L::P + h * L::PBYTES;
+          if (MODE == MODE_V) {
+            // K = 128 words: P rows are the K rows of an MN-major operand whose M (regions) chunks are 4 KB apart;
+            // M = 128 reads past the R valid regions (into the next tile): those accumulator lanes are never stored
+            const uint32_t loX = desc_lo(st + L::X, kTileBytes);
+            const uint32_t loP = desc_lo(pb, kCh32);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            mma_bf16_w(tmem, loP + ((ks * 512) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idV, (k | ks) != 0);
-        } else {
-          // K = R regions: one 16-column chunk of P per K step
-          const uint32_t loX = desc_lo(st + L::X, L::CH);
-          const uint32_t loP = desc_lo(st + L::P);
+            for (int ks = 0; ks < 8; ++ks)
+              mma_bf16_w(acc, loP + ((ks * 512) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idV, (k | ks) != 0);
+          } else {
+            // K = R regions: one 16-column chunk of P per K step
+            const uint32_t loX = desc_lo(st + L::X, L::CH);
+            const uint32_t loP = desc_lo(pb);
 #pragma unroll
-          for (int ks = 0; ks < NC; ++ks)
-            mma_bf16_w(tmem, loP + ((ks * kCh32) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idT, (k | ks) != 0);
+            for (int ks = 0; ks < NC; ++ks)
+              mma_bf16_w(acc, loP + ((ks * kCh32) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idT, (k | ks) != 0);
+          }
         }
         tc_commit(empty(s));
         if (k == n_steps - 1) tc_commit(done);
@@ -145,31 +158,33 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
     if (n_steps > 0) {
       mbar_wait(done, 0);
       tc_fence_after();
-      bool valid;
-      float* dst;
-      if (MODE == MODE_V) {
-        valid = row < R;
-        dst = a.out + ((size_t)i0 * R + row) * kD;
-      } else {
-        const long long grow = (long long)jt * kRows + row;
-        valid = grow < a.text_rows;
-        dst = a.out + (size_t)grow * kD;
-      }
-      const bool warp_valid = MODE == MODE_V ? (q * 32 < R) : true;
-      if (warp_valid) {
+      for (int h = 0; h < n_mem; ++h) {
+        bool valid;
+        float* dst;
+        if (MODE == MODE_V) {
+          valid = row < R;
+          dst = a.out + ((size_t)(m0 + h) * R + row) * kD;
+        } else {
+          const long long grow = (long long)(m0 + h) * kRows + row;
+          valid = grow < a.text_rows;
+          dst = a.out + (size_t)grow * kD;
+        }
+        const bool warp_valid = MODE == MODE_V ? (q * 32 < R) : true;
+        if (warp_valid) {
 #pragma unroll 1
-        for (int c = 0; c < kD; c += 32) {
-          float v[32];
-          tmem_ld16(tmem + lane_off + c, reinterpret_cast<uint32_t*>(v));
-          tmem_ld16(tmem + lane_off + c + 16, reinterpret_cast<uint32_t*>(v) + 16);
-          tmem_ld_wait();
-          if (valid) {
-            if (MODE == MODE_V) {
+          for (int c = 0; c < kD; c += 32) {
+            float v[32];
+            tmem_ld16(tmem + h * 256 + lane_off + c, reinterpret_cast<uint32_t*>(v));
+            tmem_ld16(tmem + h * 256 + lane_off + c + 16, reinterpret_cast<uint32_t*>(v) + 16);
+            tmem_ld_wait();
+            if (valid) {
+              if (a.accumulate) {
 #pragma unroll
-              for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + c + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
-            } else {
+                for (int x = 0; x < 32; x += 4) red_add_v4(dst + c + x, v[x], v[x + 1], v[x + 2], v[x + 3]);
+              } else {
 #pragma unroll
-              for (int x = 0; x < 32; x += 4) red_add_v4(dst + c + x, v[x], v[x + 1], v[x + 2], v[x + 3]);
+                for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + c + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+              }
             }
           }
         }
@@ -178,7 +193,7 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 256 * NP);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -210,6 +225,31 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return DVLP_OK;
 }
 
+template <int R, int MODE, int NP>
+static int launch_mode(const CUtensorMap& mP, const CUtensorMap& mX, Args a, int n_members, int k_total, int sms,
+                       bool may_split, size_t out_bytes, cudaStream_t st) {
+  using L = Lay<R, MODE, NP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_grad_gemm2<R, MODE, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
+    attr_set = true;
+  }
+  // groups x K splits ~ one wave of CTAs
+  a.n_groups = (n_members + NP - 1) / NP;
+  int splits = may_split ? sms / a.n_groups : 1;
+  if (splits < 1) splits = 1;
+  if (splits > k_total) splits = k_total;
+  a.steps_per_split = (k_total + splits - 1) / splits;
+  splits = (k_total + a.steps_per_split - 1) / a.steps_per_split;
+  if (!a.accumulate && splits > 1) {       // split partial sums need a zeroed output
+    DVLP_CUDA_OK(cudaMemsetAsync(a.out, 0, out_bytes, st));
+    a.accumulate = 1;
+  }
+  k_grad_gemm2<R, MODE, NP><<<a.n_groups * splits, kThreads, L::kAlloc, st>>>(mP, mX, a);
+  DVLP_LAUNCH_OK();
+  return DVLP_OK;
+}
+
 template <int R>
 static int launch(const void* vb, const void* tb, int Bv, int Bt, int W, char* ws, const Workspace& Lw, cudaStream_t st) {
   const int tiles = (Bt + 3) / 4;
@@ -222,29 +262,22 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, int W, char* w
   int dev = 0, sms = 148;
   DVLP_CUDA_OK(cudaGetDevice(&dev));
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static bool attr_set = false;
-  if (!attr_set) {
-    DVLP_CUDA_OK(cudaFuncSetAttribute(k_grad_gemm2<R, MODE_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<R, MODE_V>::kAlloc));
-    DVLP_CUDA_OK(cudaFuncSetAttribute(k_grad_gemm2<R, MODE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<R, MODE_T>::kAlloc));
-    attr_set = true;
-  }
   Args a{};
   a.Bv = Bv; a.Bt = Bt; a.tiles_per_video = tiles; a.text_rows = (long long)Bt * W;
-  // dV': one CTA per video
-  a.videos_per_split = Bv;
-  a.out = (float*)(ws + Lw.dvh);
-  k_grad_gemm2<R, MODE_V><<<Bv, kThreads, Lay<R, MODE_V>::kAlloc, st>>>(mP, mT, a);
-  DVLP_LAUNCH_OK();
-  // dT': text tiles x video splits ~ one wave of CTAs
-  int splits = sms / tiles;
-  if (splits < 1) splits = 1;
-  if (splits > Bv) splits = Bv;
-  a.videos_per_split = (Bv + splits - 1) / splits;
-  splits = (Bv + a.videos_per_split - 1) / a.videos_per_split;
-  a.out = (float*)(ws + Lw.dth);
-  k_grad_gemm2<R, MODE_T><<<tiles * splits, kThreads, Lay<R, MODE_T>::kAlloc, st>>>(mP, mV, a);
-  DVLP_LAUNCH_OK();
-  return DVLP_OK;
+  // Two accumulators per CTA pay once the K loops are long (many texts: the sharded global batch); at the per-GPU
+  // batch the loops are too short to amortise the second epilogue.  DVLP_GG_PAIR = 0 / 1 overrides.
+  static const int forced = [] { const char* e = getenv("DVLP_GG_PAIR"); return e ? atoi(e) : -1; }();
+  const bool pair = forced >= 0 ? forced != 0 : tiles >= 128;     // measured: -13 % at 256 tiles, break-even at 64
+  // dV' (Bv, R, d): overwritten unless split;  dT' (Bt*W, d): accumulated (the caller zeroes it)
+  a.out = (float*)(ws + Lw.dvh); a.accumulate = 0;
+  const size_t dv_bytes = (size_t)Bv * R * kD * 4;
+  rc = pair ? launch_mode<R, MODE_V, 2>(mP, mT, a, Bv, tiles, sms, true, dv_bytes, st)
+            : launch_mode<R, MODE_V, 1>(mP, mT, a, Bv, tiles, sms, false, dv_bytes, st);
+  if (rc) return rc;
+  a.out = (float*)(ws + Lw.dth); a.accumulate = 1;
+  rc = pair ? launch_mode<R, MODE_T, 2>(mP, mV, a, tiles, Bv, sms, true, 0, st)
+            : launch_mode<R, MODE_T, 1>(mP, mV, a, tiles, Bv, sms, true, 0, st);
+  return rc;
 }
 }  // namespace gg2
 
