@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_gram_tile(const __nv_bfloat16* __restri
 // (exact products, fp32 accumulate) and is scaled by inv_a inv_b afterwards, like the pair kernels do for S.
 // Block Bv + Bt (if launched) zeroes the padded tail of the text-side vectors.
 constexpr int kPrepLd = (256 + 8) * 2;     // shared-memory row stride in bytes: conflict-free ldmatrix
-__global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ t,
+__global__ void __launch_bounds__(512) k_prep_item(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ t,
                                                    const float* __restrict__ vmask, const float* __restrict__ tmask,
                                                    int Bv, int Bt, int R, int W, float lambda,
                                                    float* __restrict__ alpha, float* __restrict__ beta,
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restri
                                                    __nv_bfloat16* __restrict__ gbd, int pad_from, int pad_to) {
   extern __shared__ __align__(16) uint8_t psm[];
   __shared__ float s_inv[128];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if ((int)blockIdx.x == Bv + Bt) {            // padded tail of beta / m2t (whole 128-row tiles are bulk-copied)
     for (int e = pad_from + threadIdx.x; e < pad_to; e += blockDim.x) { beta[e] = 0.f; m2t[e] = 0.f; }
     // rows of the missing texts in the last block-diagonal Gram tile
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restri
   }
   __syncthreads();
   // inverse norms: one warp per row, 8 elements per lane
-  for (int row = warp; row < L; row += 8) {
+  for (int row = warp; row < L; row += nwarp) {
     const uint4 val = *reinterpret_cast<const uint4*>(psm + row * kPrepLd + lane * 16);
     const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
     float ss = 0.f;
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restri
     const float a = 1.f / (sqrtf(ss) + kEps);
     if (lane == 0) { s_inv[row] = a; inv_out[row] = a; }
   }
-  // mask terms (warp 7; see k_mask_terms)
-  if (warp == 7) {
+  // mask terms (last warp; see k_mask_terms)
+  if (warp == nwarp - 1) {
     float mx = -INFINITY;
     for (int c = lane; c < L; c += 32) mx = fmaxf(mx, mask[c]);
     mx = warp_max(mx);
@@ -206,9 +206,10 @@ __global__ void __launch_bounds__(256) k_prep_item(const __nv_bfloat16* __restri
   __syncthreads();
   // Gram: 16 x 16 output tiles, upper triangle computed and mirrored
   const int nt = L >> 4;
-  for (int tile = warp; tile < nt * nt; tile += 8) {
-    const int ti = tile / nt, tj = tile - ti * nt;
-    if (tj < ti) continue;
+  for (int tile = warp; tile < nt * (nt + 1) / 2; tile += nwarp) {     // upper-triangular tiles only
+    int ti = 0, tj = tile;
+    while (tj >= nt - ti) { tj -= nt - ti; ++ti; }
+    tj += ti;
     float acc[2][4] = {};
 #pragma unroll 4
     for (int k0 = 0; k0 < 256; k0 += 16) {
@@ -310,7 +311,7 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
       attr_set = true;
     }
     const bool pad = nt_pad > (size_t)Bt * W;
-    k_prep_item<<<Bv + Bt + (pad ? 1 : 0), 256, smem, st>>>(
+    k_prep_item<<<Bv + Bt + (pad ? 1 : 0), Lmax > 64 ? 512 : 256, smem, st>>>(
         vb, tb, im_mask, s_mask, Bv, Bt, R, W, lambda, alpha, beta, mv, mt, (float*)(ws + L.m2v), (float*)(ws + L.m2t),
         (__nv_bfloat16*)(ws + L.gvb), (__nv_bfloat16*)(ws + L.gtb), W == 32 ? (__nv_bfloat16*)(ws + L.gbd) : nullptr, Bt * W,
         (int)nt_pad);
