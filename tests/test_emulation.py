@@ -56,3 +56,18 @@ def test_rwa_tail_matches_autograd():
     l2, d = emul.rwa_loss_fwd_bwd(sc.detach())
     assert abs(l2.item() - loss.item()) < 1e-12
     assert rel_err(d, sc.grad) < 1e-12
+
+
+@pytest.mark.parametrize("focal", ["equal", "prob"])
+@pytest.mark.parametrize("shape", [(2, 288, 64, 3, 96, 64), (2, 240, 99, 2, 96, 128), (2, 30, 99, 3, 96, 128),
+                                   (3, 17, 9, 4, 16, 16)])
+def test_chunked_large_shape_plan_matches_oracle(shape, focal):
+    """The data flow planned for the large-shape kernel: zero-padded regions / words with the real
+    counts in thresholds and means, two passes over S, Gram-form denominators accumulated block by block."""
+    from tests import emul_chunked
+    Bv, R, W, Bt, C, Wt = shape
+    b = synth.make_batch(Bv, R, W, 32, 7, 0.2, Bt=Bt)
+    want = O.pair_scores(b.im.double(), b.s.double(), b.im_mask.double(), b.s_mask.double(), focal=focal)
+    got = emul_chunked.scores_chunked(b.im.double(), b.s.double(), b.im_mask, b.s_mask, C=C, Wt=Wt,
+                                      focal=(focal == "equal"))
+    assert (got - want).abs().max() < 1e-6
