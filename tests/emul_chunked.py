@@ -90,3 +90,80 @@ def scores_chunked(im, s, im_mask, s_mask, **kw):
         for j in range(Bt):
             out[i, j] = pair_score_chunked(im[i], s[j], im_mask[i].to(im.dtype), s_mask[j].to(im.dtype), **kw)
     return out
+
+
+def forward_backward_padded(im, s, im_mask, s_mask, d_scores, C=96, Wt=128, lam=20.0, focal=True):
+    """Kernel-style forward + hand-derived backward (tests/emul.py's Gram form) on ZERO-PADDED items, with what the
+    planned kernel needs on top of the small-shape one:
+
+      * real counts in the focal thresholds and in the means;
+      * padded QUERIES (word rows >= W in the i2t direction, region columns >= R in the t2i direction) carry no
+        gradient: their upstream factor gamma is forced to zero (their cosine is 0 / den, den > 0);
+      * the inverse norm of a zero row is 1 / eps = 1e8: it only ever multiplies exact zeros on the way to REAL rows.
+
+    Returns (scores, d_im, d_s) for the real rows."""
+    Bv, R, d = im.shape
+    Bt, W, _ = s.shape
+    dt = im.dtype
+    Rp = (R + C - 1) // C * C
+    Wp = (W + Wt - 1) // Wt * Wt
+    imp = torch.zeros(Bv, Rp, d, dtype=dt); imp[:, :R] = im
+    sp = torch.zeros(Bt, Wp, d, dtype=dt); sp[:, :W] = s
+    mvp = torch.full((Bv, Rp), PAD_MASK, dtype=dt); mvp[:, :R] = im_mask.to(dt)
+    mtp = torch.full((Bt, Wp), PAD_MASK, dtype=dt); mtp[:, :W] = s_mask.to(dt)
+    mvp = mvp - im_mask.to(dt).max(1, keepdim=True).values
+    mtp = mtp - s_mask.to(dt).max(1, keepdim=True).values
+    alpha = 1.0 / (imp.norm(dim=-1, keepdim=True) + EPS); beta = 1.0 / (sp.norm(dim=-1, keepdim=True) + EPS)
+    Vh, Th = imp * alpha, sp * beta
+    GV = torch.einsum("ird,isd->irs", Vh, Vh); GT = torch.einsum("jwd,jxd->jwx", Th, Th)
+    S = torch.einsum("ird,jwd->ijrw", Vh, Th)
+    neg = S <= 0
+    l = torch.where(neg, 0.1 * S, S)
+    mv = mvp[:, None, :, None]; mt = mtp[None, :, None, :]
+    rvalid = (torch.arange(Rp) < R).to(dt)[None, None, :, None]       # real regions
+    wvalid = (torch.arange(Wp) < W).to(dt)[None, None, None, :]       # real words
+
+    def direction(ctx_dim, n_ctx_real, mask, G, eq):
+        q_dim = 5 - ctx_dim
+        nrm = l.square().sum(q_dim, keepdim=True).sqrt() + EPS
+        A = l / nrm
+        e = torch.exp(lam * (A + mask) - lam)
+        E = e.sum(ctx_dim, keepdim=True)
+        H = (e * n_ctx_real > E) if focal else torch.ones_like(e, dtype=torch.bool)
+        u = torch.where(H, e, torch.zeros_like(e))                    # un-normalised, as the kernels keep it
+        num = (u * S).sum(ctx_dim, keepdim=True)
+        Y = torch.einsum(eq, G, u)
+        D = (u * Y).sum(ctx_dim, keepdim=True)
+        den = D.clamp_min(1e-30).sqrt()
+        cos = torch.where(D > 1e-30, num / den, torch.zeros_like(num))
+        return dict(nrm=nrm, A=A, u=u, Y=Y, D=D, den=den, cos=cos, q_dim=q_dim)
+
+    dA = direction(2, R, mv, GV, "irs,ijsw->ijrw")     # i2t: context = regions, query = words
+    dB = direction(3, W, mt, GT, "jwx,ijrx->ijrw")     # t2i: context = words, query = regions
+    scores = (dA["cos"] * wvalid).sum(3).squeeze(2) / W + (dB["cos"] * rvalid).sum(2).squeeze(-1) / R
+    g = d_scores[:, :, None, None]
+
+    def backward(D_, gam):
+        # gam: upstream factor per query (0 for padded queries)
+        c1 = gam / D_["den"]
+        kap = D_["cos"] / D_["den"]
+        dAtt = lam * c1 * D_["u"] * (S - kap * D_["Y"])
+        t = (D_["A"] * dAtt).sum(D_["q_dim"], keepdim=True)
+        dl = (dAtt - D_["A"] * t) / D_["nrm"]
+        dS = dl * torch.where(neg, torch.full_like(S, 0.1), torch.ones_like(S)) + c1 * D_["u"]
+        dD = -gam * D_["cos"] / (2 * D_["D"].clamp_min(1e-30))
+        return dS, dD
+
+    dS_A, dD_A = backward(dA, g / W * wvalid)
+    dS_B, dD_B = backward(dB, g / R * rvalid)
+    P = dS_A + dS_B
+    dVh = torch.einsum("ijrw,jwd->ird", P, Th)
+    dTh = torch.einsum("ijrw,ird->jwd", P, Vh)
+    dGV = torch.einsum("ijrw,ijsw->irs", dA["u"] * dD_A, dA["u"])
+    dGT = torch.einsum("ijrw,ijrx->jwx", dB["u"] * dD_B, dB["u"])
+    dVh = dVh + 2 * torch.einsum("irs,isd->ird", dGV, Vh)
+    dTh = dTh + 2 * torch.einsum("jwx,jxd->jwd", dGT, Th)
+    d_im = alpha * (dVh - Vh * (Vh * dVh).sum(-1, keepdim=True))
+    d_s = beta * (dTh - Th * (Th * dTh).sum(-1, keepdim=True))
+    assert torch.isfinite(d_im[:, :R]).all() and torch.isfinite(d_s[:, :W]).all()
+    return scores, d_im[:, :R], d_s[:, :W]
