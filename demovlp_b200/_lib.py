@@ -25,6 +25,8 @@ SYMBOLS = {
     "dvlp_last_cuda_error": (_i, []),
     "dvlp_rw_tcgen05_supported": (_i, [_i, _i, _i]),
     "dvlp_set_default_impl": (None, [_i]),
+    "dvlp_rw_bwd_out_dtype_supported": (_i, [_i, _i, _i, _i, _f, _i]),
+    "dvlp_debug_set_trace": (None, [_p]),
     "dvlp_launch_count": (C.c_uint64, []),
     "dvlp_profile_enable": (None, [_i]),
     "dvlp_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -40,6 +42,7 @@ SYMBOLS = {
     "dvlp_ranks_t2v": (_i, [_p, _i, _i, _p, _p]),
     "dvlp_ranks_v2t": (_i, [_p, _i, _i, _p, _p]),
     "dvlp_p2p_control_bytes": (_sz, []),
+    "dvlp_p2p_check": (_i, [_p, _p]),
     "dvlp_p2p_allgather": (_i, [_p, _i, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), _p]),
     "dvlp_p2p_sum_scalar": (_i, [_p, _i, _i, _p, _p, _p]),
     "dvlp_p2p_reduce_scatter": (_i, [_p, _i, _i, _sz, _sz, _p, _i, _p]),

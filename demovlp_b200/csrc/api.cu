@@ -50,6 +50,7 @@ int run_ranks_v2t(const double*, int, int, double*, cudaStream_t);
 int run_p2p_allgather(void* const*, int, int, int, const void* const*, const size_t*, const size_t*, cudaStream_t);
 int run_p2p_sum_scalar(void* const*, int, int, const float*, float*, cudaStream_t);
 int run_p2p_reduce_scatter(void* const*, int, int, size_t, size_t, void*, int, cudaStream_t);
+int run_p2p_check(const void*, cudaStream_t);
 // tcgen05 path: pair_fwd2.cu, pair_bwd2.cu, grad_gemm2.cu
 int run_pair_fwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
                   float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
@@ -117,10 +118,19 @@ static int check_common(const void* im, const void* s, const float* im_mask, con
   return DVLP_OK;
 }
 
-static int pick_tc(int impl, int R, int W, int d, bool* tc) {
+// The tcgen05 kernels evaluate exp(lambda (A - 1)) with the FIXED maximum lambda (A <= 1) instead of a running row
+// maximum: beyond this bound a row of small attentions could underflow entirely (the reference's max-subtracting
+// softmax would not), so such calls go to the generic kernels (auto) or are refused (explicit tcgen05).
+constexpr float kMaxLambdaTc = 40.f;
+
+static int pick_tc(int impl, int R, int W, int d, bool* tc, float lambda = 20.f) {
   if (impl == DVLP_IMPL_AUTO) impl = g_default_impl.load();
   if (impl == DVLP_IMPL_GENERIC) { *tc = false; return DVLP_OK; }
   bool ok = tc_supported(R, W, d);
+  if (!(lambda > 0.f && lambda <= kMaxLambdaTc)) {
+    if (impl == DVLP_IMPL_TCGEN05) return DVLP_ERR_BAD_ARG;
+    ok = false;
+  }
   if (impl == DVLP_IMPL_TCGEN05 && !ok) return DVLP_ERR_BAD_SHAPE;
   if (impl != DVLP_IMPL_AUTO && impl != DVLP_IMPL_TCGEN05) return DVLP_ERR_BAD_ARG;
   *tc = ok;
@@ -128,15 +138,16 @@ static int pick_tc(int impl, int R, int W, int d, bool* tc) {
 }
 
 static int device_ok() {
-  static int cached = 1;   // 1 = unknown
-  if (cached != 1) return cached;
+  // per device: a process may drive several GPUs (the result of device 0 says nothing about device 1)
+  static std::atomic<unsigned long long> ok_mask{0};
   int dev = 0;
-  cudaDeviceProp p;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
-    return cached = DVLP_ERR_NO_DEVICE;
-  }
-  cached = (p.major == 10) ? DVLP_OK : DVLP_ERR_NO_DEVICE;
-  return cached;
+  if (cudaGetDevice(&dev) != cudaSuccess) return DVLP_ERR_NO_DEVICE;
+  if (dev >= 0 && dev < 64 && ((ok_mask.load(std::memory_order_acquire) >> dev) & 1ull)) return DVLP_OK;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10)
+    return DVLP_ERR_NO_DEVICE;
+  if (dev >= 0 && dev < 64) ok_mask.fetch_or(1ull << dev, std::memory_order_release);
+  return DVLP_OK;
 }
 
 }  // namespace dvlp
@@ -158,6 +169,7 @@ const char* dvlp_error_string(int code) {
     case DVLP_ERR_CUDA: return "CUDA error";
     case DVLP_ERR_NO_DEVICE: return "no sm_100 CUDA device (no CPU fallback exists)";
     case DVLP_ERR_BAD_ARG: return "bad argument";
+    case DVLP_ERR_TIMEOUT: return "peer-memory exchange timed out (a rank is missing or late beyond DVLP_P2P_TIMEOUT_S)";
   }
   return "unknown error";
 }
@@ -167,7 +179,7 @@ int dvlp_rw_tcgen05_supported(int R, int W, int d) { return tc_supported(R, W, d
 void dvlp_set_default_impl(int impl) { g_default_impl.store(impl); }
 uint64_t dvlp_launch_count(void) { return g_launches.load(); }
 
-/* debug only (not in the public header): device buffer of 5*32*16 int64 clock stamps, see pair_tc_bwd.cu */
+/* debug only: device buffer of 5*32*16 int64 clock stamps written by pair_bwd2.cu (tools/trace_tiles.py) */
 void dvlp_debug_set_trace(void* dev_buffer) { g_trace_buffer = dev_buffer; }
 
 void dvlp_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
@@ -209,7 +221,7 @@ static int scores_fwd(const void* im, const void* s, const float* im_mask, const
   if (rc) return rc;
   if (!scores) return DVLP_ERR_NULL_POINTER;
   bool tc = false;
-  if ((rc = pick_tc(impl, R, W, d, &tc))) return rc;
+  if ((rc = pick_tc(impl, R, W, d, &tc, lambda))) return rc;
   if ((rc = device_ok())) return rc;
   Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc, train);
   if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
@@ -259,7 +271,7 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   if (!d_scores || !d_im || !d_s) return DVLP_ERR_NULL_POINTER;
   if (out_dtype != DVLP_F32 && out_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
   bool tc = false;
-  if ((rc = pick_tc(impl, R, W, d, &tc))) return rc;
+  if ((rc = pick_tc(impl, R, W, d, &tc, lambda))) return rc;
   if ((rc = device_ok())) return rc;
   Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc, true);
   if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
@@ -369,7 +381,20 @@ int dvlp_ranks_v2t(const double* sims, int Nq, int Nv, double* ranks, void* stre
   return run_ranks_v2t(sims, Nq, Nv, ranks, (cudaStream_t)stream);
 }
 
+int dvlp_rw_bwd_out_dtype_supported(int impl, int R, int W, int d, float lambda, int out_dtype) {
+  if (out_dtype == DVLP_F32) return 1;
+  if (out_dtype != DVLP_BF16) return 0;
+  bool tc = false;
+  if (pick_tc(impl, R, W, d, &tc, lambda) != DVLP_OK || !tc) return 0;
+  return (d == 256 && (R % 16) == 0 && (W % 16) == 0 && R <= 128 && W <= 128) ? 1 : 0;   // run_grad_finalize_tc
+}
+
 size_t dvlp_p2p_control_bytes(void) { return 4096; }
+
+int dvlp_p2p_check(const void* own_arena, void* stream) {
+  if (!own_arena) return DVLP_ERR_NULL_POINTER;
+  return run_p2p_check(own_arena, (cudaStream_t)stream);
+}
 
 int dvlp_p2p_allgather(void* const* peer_arenas, int world, int rank, int n_tensors, const void* const* shards_host,
                        const size_t* shard_bytes_host, const size_t* arena_offsets_host, void* stream) {

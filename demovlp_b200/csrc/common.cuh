@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/demovlp_b200.h"
 
 namespace dvlp {
@@ -65,6 +67,21 @@ struct ProfScope {
   void* rec;
   ProfScope(int slot, cudaStream_t st);
   ~ProfScope();
+};
+
+// cudaFuncSetAttribute (and the sm_100 check) are PER DEVICE: remembers on which devices of this process a
+// one-time setup has run (device ids < 64; beyond that the setup simply repeats, which is harmless).
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool pending() const {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    return !((mask.load(std::memory_order_acquire) >> dev) & 1ull);
+  }
+  void done() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+  }
 };
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

@@ -229,10 +229,10 @@ template <int R, int MODE, int NP>
 static int launch_mode(const CUtensorMap& mP, const CUtensorMap& mX, Args a, int n_members, int k_total, int sms,
                        bool may_split, size_t out_bytes, cudaStream_t st) {
   using L = Lay<R, MODE, NP>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     DVLP_CUDA_OK(cudaFuncSetAttribute(k_grad_gemm2<R, MODE, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
-    attr_set = true;
+    attr_once.done();
   }
   // groups x K splits ~ one wave of CTAs
   a.n_groups = (n_members + NP - 1) / NP;

@@ -609,11 +609,11 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, float lambda, 
   DVLP_CUDA_OK(cudaGetDevice(&dev));
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int grid = (int)(a.total_units < sms ? a.total_units : sms);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     DVLP_CUDA_OK(cudaFuncSetAttribute(k_pair_bwd2<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
     DVLP_CUDA_OK(cudaFuncSetAttribute(k_pair_bwd2<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
-    attr_set = true;
+    attr_once.done();
   }
   if (a.trace)      // debugging aid (tools/trace_tiles.py): the instrumented instantiation
     k_pair_bwd2<R, true><<<grid, L::kThreads, L::kAlloc, st>>>(mV, mT, mGV, mGBD, mP, a);

@@ -481,10 +481,10 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, float lambda, 
   DVLP_CUDA_OK(cudaGetDevice(&dev));
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int grid = (int)(a.total_units < sms ? a.total_units : sms);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     DVLP_CUDA_OK(cudaFuncSetAttribute(k_pair_fwd2<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
-    attr_set = true;
+    attr_once.done();
   }
   k_pair_fwd2<R><<<grid, L::kThreads, L::kAlloc, st>>>(mV, mT, mGV, mGBD, a);
   DVLP_LAUNCH_OK();

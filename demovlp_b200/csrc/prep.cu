@@ -305,10 +305,10 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
   if (fused) {
     const int Lmax = R > W ? R : W;
     const size_t smem = (size_t)Lmax * kPrepLd;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.pending()) {
       DVLP_CUDA_OK(cudaFuncSetAttribute(k_prep_item, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kPrepLd));
-      attr_set = true;
+      attr_once.done();
     }
     const bool pad = nt_pad > (size_t)Bt * W;
     k_prep_item<<<Bv + Bt + (pad ? 1 : 0), Lmax > 64 ? 512 : 256, smem, st>>>(
@@ -332,10 +332,10 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
     DVLP_LAUNCH_OK();
     const size_t smem = (size_t)sd.Lc * (d + 1) * 4;
     if (smem <= 200 * 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      static DeviceOnce attr_once;
+      if (attr_once.pending()) {
         DVLP_CUDA_OK(cudaFuncSetAttribute(k_gram_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_once.done();
       }
       k_gram_tile<<<sd.items, 256, smem, st>>>(sd.x, sd.inv, sd.Lc, d, full ? sd.G : nullptr, sd.Gb);
     } else {

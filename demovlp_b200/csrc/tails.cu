@@ -439,11 +439,11 @@ static int sim_bwd_t(const T* a, const T* b, int N, int M, int d, float eps, con
   DVLP_LAUNCH_OK();
   k_inv_norm_max<T><<<(M + 7) / 8, 256, 0, st>>>(b, M, d, eps, ib);
   DVLP_LAUNCH_OK();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     DVLP_CUDA_OK(cudaFuncSetAttribute(k_sim_bwd_side<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DVLP_CUDA_OK(cudaFuncSetAttribute(k_sim_bwd_side<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_once.done();
   }
   if ((size_t)(N > M ? N : M) * kSimRB * 4 > 200 * 1024) return DVLP_ERR_BAD_SHAPE;
   if (d_a) {

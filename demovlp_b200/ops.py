@@ -2,8 +2,6 @@
 the arithmetic is all in libdemovlp_b200.so)."""
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import _lib
@@ -61,8 +59,9 @@ def rw_scores_bwd_raw(state, d_scores, out_dtype=torch.float32, d_s_out=None):
     Bv, R, d = im.shape
     Bt, W, _ = s.shape
     d_scores = d_scores.to(torch.float32).contiguous()
-    direct = (out_dtype == torch.bfloat16 and impl != _lib.IMPL_GENERIC and lib.dvlp_rw_tcgen05_supported(R, W, d)
-              and os.environ.get("DVLP_TC_BWD", "2") != "0" and d_s_out is None)
+    # the library decides whether its finalisation can write bf16 for this impl / shape (one source of truth)
+    direct = (out_dtype == torch.bfloat16 and d_s_out is None
+              and bool(lib.dvlp_rw_bwd_out_dtype_supported(impl, R, W, d, float(lam), _lib.BF16)))
     odt = torch.bfloat16 if direct else torch.float32
     d_im = torch.empty(Bv, R, d, dtype=odt, device=im.device)
     if d_s_out is not None:

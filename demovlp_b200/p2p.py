@@ -46,6 +46,7 @@ class PeerExchange:
         self.key = None
         self.calls = 0
         self.slot_call = [-1] * N_SLOTS
+        self.last_reduce_call = -1
 
     # ------------------------------------------------------------------ arena
     def ensure(self, shard_specs, reduce_shard_shape):
@@ -91,6 +92,7 @@ class PeerExchange:
         self.key = key
         self.calls = 0
         self.slot_call = [-1] * N_SLOTS
+        self.last_reduce_call = -1
 
     def _view(self, off, nbytes, dtype, shape):
         return self.arena[off:off + nbytes].view(dtype).view(shape)
@@ -135,8 +137,21 @@ class PeerExchange:
         _lib.check(rc, "p2p_sum_scalar")
         return out
 
+    def check_errors(self):
+        """Raise if a peer-memory wait of this rank ever timed out (DVLP_P2P_TIMEOUT_S).  Synchronises the stream:
+        call it at a point where the host waits anyway (e.g. where the trainer reads ``loss.item()``)."""
+        with torch.cuda.device(self.device):
+            rc = _lib.load().dvlp_p2p_check(_lib.ptr(self.arena), _lib.stream_ptr())
+        _lib.check(rc, "p2p_check")
+
     def reduce_buffer(self):
-        """fp32 (world * b, ...) region of the arena the backward writes its text-gradient partial sums into."""
+        """fp32 (world * b, ...) region of the arena the backward writes its text-gradient partial sums into.
+        The region is single-buffered: a second backward before another forward (gather) has ordered the peers'
+        reads of the previous reduce-scatter could overwrite it, so that sequence is refused."""
+        if self.last_reduce_call == self.calls:
+            raise RuntimeError("demovlp_b200: two sharded backwards without a forward in between share the single "
+                               "reduce-scatter region of the peer arena; set DVLP_P2P=0 to use the NCCL transport")
+        self.last_reduce_call = self.calls
         shp = (self.world * self.red_shard_shape[0],) + self.red_shard_shape[1:]
         return self._view(self.red_off, 4 * self.red_shard_floats * self.world, torch.float32, shp)
 

@@ -40,6 +40,7 @@ extern "C" {
 #define DVLP_ERR_CUDA (-6)           /* a CUDA call failed (see dvlp_last_cuda_error)    */
 #define DVLP_ERR_NO_DEVICE (-7)      /* no sm_100 device: there is NO CPU fallback       */
 #define DVLP_ERR_BAD_ARG (-8)        /* other invalid argument                           */
+#define DVLP_ERR_TIMEOUT (-9)        /* a peer-memory exchange gave up waiting for a rank */
 
 /* implementation selector for the scoring kernels (debug / A-B testing) */
 #define DVLP_IMPL_AUTO 0     /* tcgen05 path when the shape qualifies, else generic    */
@@ -54,6 +55,12 @@ int dvlp_last_cuda_error(void);
 int dvlp_rw_tcgen05_supported(int R, int W, int d);
 /* process-wide default for `impl` arguments given as DVLP_IMPL_AUTO. */
 void dvlp_set_default_impl(int impl);
+/* 1 when dvlp_rw_scores_bwd can write its gradients in `out_dtype` for this impl / shape / lambda
+ * (DVLP_F32 always; DVLP_BF16 only where the tcgen05 finalisation kernel serves the shape). */
+int dvlp_rw_bwd_out_dtype_supported(int impl, int R, int W, int d, float lambda, int out_dtype);
+/* debugging aid: device buffer (5*32*16 int64) that the backward pair kernel of CTA 0 fills with per-phase clock
+ * stamps (tools/trace_tiles.py); NULL (default) disables it.  Not part of the reference-facing surface. */
+void dvlp_debug_set_trace(void* dev_buffer);
 /* number of kernels this library has launched so far in this process. */
 uint64_t dvlp_launch_count(void);
 
@@ -175,8 +182,12 @@ int dvlp_ranks_v2t(const double* sims, int Nq, int Nv, double* ranks, void* stre
  *                            of rows [rank * shard_floats, (rank + 1) * shard_floats), added in rank order.
  * A data region may be overwritten again only after a later exchange of the same call sequence has completed
  * (the sharded loss alternates allgather -> sum_scalar -> reduce_scatter).
+ * Flag waits are bounded by wall time: DVLP_P2P_TIMEOUT_S seconds (environment, default 600).  A wait that gives up
+ * does NOT trap: it records a sticky error word in this rank's control block, the kernels finish with meaningless
+ * data, and dvlp_p2p_check (which synchronises `stream`) returns DVLP_ERR_TIMEOUT from then on.
  */
 size_t dvlp_p2p_control_bytes(void);
+int dvlp_p2p_check(const void* own_arena, void* stream);
 int dvlp_p2p_allgather(void* const* peer_arenas, int world, int rank, int n_tensors, const void* const* shards_host,
                        const size_t* shard_bytes_host, const size_t* arena_offsets_host, void* stream);
 int dvlp_p2p_sum_scalar(void* const* peer_arenas, int world, int rank, const float* value, float* out, void* stream);

@@ -17,8 +17,20 @@ GRAD_TOL = 1e-2       # north star: gradients within 1e-2 relative
 IMPLS = ["generic", "auto"]
 
 
+MAX_RANK_FLIPS_96 = 10    # end-to-end t2v rank flips tolerated on the 96 x 96 eval fixture (count is recorded)
+
+
 def dev(b):
     return b.to("cuda")
+
+
+def _record(kind, payload):
+    """Append a measured quantity to gpurun_out/r2_parity_records.jsonl (copied into profiles/ after a GPU run)."""
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r2_parity_records.jsonl"), "a") as f:
+        f.write(json.dumps({"kind": kind, **payload}) + "\n")
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -54,7 +66,7 @@ def test_loss_and_gradients_match_reference_fixture(name, impl):
     loss, gl, ll = mod(gsim, im, s, d.im_mask, d.s_len, d.s_mask)
     loss.backward()
     got = np.array([loss.item(), gl.item(), ll.item()])
-    assert np.abs(got - g["losses"]).max() < SCORE_TOL * max(1.0, np.abs(g["losses"]).max()), (got, g["losses"])
+    assert np.abs(got - g["losses"]).max() < SCORE_TOL, (got, g["losses"])        # 2e-3 ABSOLUTE (north star)
     assert np.abs(gsim.detach().cpu().numpy() - g["global_sim"]).max() < 1e-5
     assert rel_err(gsim.grad.cpu(), g["d_global_sim"]) < GRAD_TOL
     if "d_im" in g:
@@ -106,9 +118,9 @@ def test_config2_full_size_vs_oracle(impl):
     loss.backward()
     tol = GENERIC_TOL if impl == "generic" else SCORE_TOL
     assert (scores.detach().cpu() - want_scores).abs().max() < tol
-    assert abs(loss.item() - want_loss) < SCORE_TOL * max(1.0, abs(want_loss))
-    assert rel_err(im.grad.float().cpu(), want_dim) < GRAD_TOL + 4e-3   # + bf16 rounding of the returned grad
-    assert rel_err(s.grad.float().cpu(), want_ds) < GRAD_TOL + 4e-3
+    assert abs(loss.item() - want_loss) < SCORE_TOL
+    assert rel_err(im.grad.float().cpu(), want_dim) < GRAD_TOL
+    assert rel_err(s.grad.float().cpu(), want_ds) < GRAD_TOL
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -246,7 +258,10 @@ def test_eval_matrix_end_to_end(impl):
     mism = int((ranks != e["t2v_ranks"]).sum())
     print(f"[eval_96/{impl}] end-to-end t2v rank mismatches vs reference matrix: {mism}/96, "
           f"max |rank diff| {np.abs(ranks - e['t2v_ranks']).max()}")
-    assert mism <= 10
+    _record("eval_rank_mismatch", dict(case="eval_96", impl=impl, mismatches=mism, rows=96,
+                                       max_abs_rank_diff=int(np.abs(ranks - e["t2v_ranks"]).max()),
+                                       max_abs_score_err=float(np.abs(local - e["local"]).max())))
+    assert mism <= MAX_RANK_FLIPS_96
     got = M.t2v_metrics(full)
     keys = [str(k) for k in e["keys"]]
     ref = dict(zip(keys, e["t2v"]))

@@ -115,3 +115,19 @@ def test_oracle_sim_matrix_and_metrics_vs_live_reference():
         for k in r:
             assert float(r[k]) == pytest.approx(o[k], rel=1e-12)
             assert float(r2[k]) == pytest.approx(o2[k], rel=1e-12)
+
+
+def test_oracle_port_matches_config3_fixture_rows():
+    """The restatement against the config-3 fixture (unmodified reference in 16-row blocks, B = 1024): the fully stored
+    score rows, i.e. one video of every 128-row shard against all 1024 texts."""
+    from demovlp_b200 import synth
+    from tests import c3_check
+    if not c3_check.available():
+        pytest.skip("tests/golden/c3_global.npz missing")
+    g = c3_check.load()
+    B, R, W, d, seed = (int(x) for x in g["meta"][:5])
+    b = synth.make_batch(B, R, W, d, seed, float(g["meta"][5]))
+    keep = [int(k) for k in g["keep_rows"]]
+    sc = O.pair_scores(b.im[keep], b.s, b.im_mask[keep], b.s_mask, 20.0, "equal")
+    assert np.abs(sc.numpy() - g["score_rows"]).max() < 5e-6
+    assert np.abs(sc.numpy()[np.arange(len(keep)), keep] - g["score_diag"][keep]).max() < 5e-6
