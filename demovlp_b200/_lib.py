@@ -24,6 +24,7 @@ SYMBOLS = {
     "dvlp_error_string": (C.c_char_p, [_i]),
     "dvlp_last_cuda_error": (_i, []),
     "dvlp_rw_tcgen05_supported": (_i, [_i, _i, _i]),
+    "dvlp_rw_path": (_i, [_i, _i, _i, _i]),
     "dvlp_set_default_impl": (None, [_i]),
     "dvlp_rw_bwd_out_dtype_supported": (_i, [_i, _i, _i, _i, _f, _i]),
     "dvlp_debug_set_trace": (None, [_p]),

@@ -35,6 +35,10 @@ ProfScope::~ProfScope() {
 
 int run_prep(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, bool, bool, char*,
              const Workspace&, cudaStream_t);
+int run_prep3(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, char*,
+              const Workspace&, cudaStream_t);
+int run_pair_fwd3(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
+                  float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
 int run_pair_generic(bool backward, const PairArgs& a, int n_cta, cudaStream_t st);
 int run_grad_finalize(const void*, int, const float*, const float*, const float*, int, int, int, int, float*,
                       cudaStream_t);
@@ -63,10 +67,11 @@ void* g_trace_buffer = nullptr;   // set through dvlp_debug_set_trace (tools/tra
 // shapes served by the tcgen05 kernels: d = 256, W = 32 words, R a multiple of 16 in [32, 80]
 bool tc_supported(int R, int W, int d) { return d == 256 && W == 32 && (R == 80 || R == 64 || R == 48 || R == 32); }
 
-Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc, bool train) {
+Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int path, bool train) {
   Workspace L{};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  const bool tc = path != kPathGeneric, tc2 = path == kPathTc2, tc3 = path == kPathTc3;
   const size_t nv = (size_t)Bv * R, nt = (size_t)Bt * W;
   // text-side vectors are padded to whole 128-row tiles (the tcgen05 kernel bulk-copies tiles)
   const size_t nt_pad = (nt + 127) / 128 * 128;
@@ -75,7 +80,7 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   L.mterm_v = take(nv * 4);
   L.mterm_t = take(nt_pad * 4);
   // (train == false: forward-only layout -- nothing the backward alone needs is allocated)
-  const bool generic_rows = train || !tc;       // fp32 normalised rows / Gram matrices of the generic kernels
+  const bool generic_rows = (train && !tc3) || !tc;   // fp32 normalised rows / Gram matrices of the generic kernels
   L.vh = take(generic_rows ? nv * d * 4 : 0);
   L.th = take(generic_rows ? nt * d * 4 : 0);
   L.gv = take(generic_rows ? nv * R * 4 : 0);
@@ -83,7 +88,7 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   bool copy = tc && in_dtype == DVLP_F32;
   L.vb = take(copy ? nv * d * 2 : 0);
   L.tb = take(copy ? nt * d * 2 : 0);
-  L.gvb = take(tc ? nv * R * 2 : 0);
+  L.gvb = take(tc2 ? nv * R * 2 : 0);
   L.gtb = take(tc ? nt_pad * W * 2 : 0);
   L.m2v = take(tc ? nv * 4 : 0);
   L.m2t = take(tc ? nt_pad * 4 : 0);
@@ -93,10 +98,20 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   L.dgt = take(train ? nt * W * 4 : 0);
   {
     const size_t units = (size_t)Bv * ((Bt + 3) / 4);
-    L.pa = take(tc && train ? units * R * 128 * 2 : 0);
-    L.rowv = take(tc && train ? units * 128 * 16 : 0);
-    L.colv = take(tc && train ? units * 4 * R * 16 : 0);
-    L.gbd = take(tc ? (size_t)((Bt + 3) / 4) * 128 * 128 * 2 : 0);
+    L.pa = take(tc2 && train ? units * R * 128 * 2 : 0);
+    L.rowv = take(tc2 && train ? units * 128 * 16 : 0);
+    L.colv = take(tc2 && train ? units * 4 * R * 16 : 0);
+    L.gbd = take(tc2 ? (size_t)((Bt + 3) / 4) * 128 * 128 * 2 : 0);
+  }
+  if (tc3) {
+    Shape3 s3{};
+    shape3(R, W, d, &s3);
+    const size_t tiles = (size_t)(Bt + s3.TPT - 1) / s3.TPT;
+    L.alpha3 = take((size_t)Bv * s3.Rp * 4);
+    L.m2v3 = take((size_t)Bv * s3.Rp * 4);
+    L.beta3 = take(tiles * 128 * 4);
+    L.m2t3 = take(tiles * 128 * 4);
+    L.gbd3 = take(tiles * 128 * 128 * 2);
   }
   // generic kernels (also the backward fallback of the tcgen05 forward): per-CTA scratch
   long long pairs = (long long)Bv * Bt;
@@ -104,7 +119,7 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool
   L.n_cta = (int)(pairs < (long long)sms * 4 ? pairs : (long long)sms * 4);
   int Lmax = R > W ? R : W;
   L.scratch_per_cta = align_up(((size_t)4 * R * W + 5 * Lmax) * 4) / 4;
-  L.scratch = take((size_t)L.n_cta * L.scratch_per_cta * 4);
+  L.scratch = take(tc3 ? 0 : (size_t)L.n_cta * L.scratch_per_cta * 4);
   L.total = off;
   return L;
 }
@@ -122,18 +137,28 @@ static int check_common(const void* im, const void* s, const float* im_mask, con
 // maximum: beyond this bound a row of small attentions could underflow entirely (the reference's max-subtracting
 // softmax would not), so such calls go to the generic kernels (auto) or are refused (explicit tcgen05).
 constexpr float kMaxLambdaTc = 40.f;
+// the large-shape kernels (pair_fwd3.cu) serve the forward; their backward partner is selected here once it exists
+constexpr bool kTc3Train = false;
 
-static int pick_tc(int impl, int R, int W, int d, bool* tc, float lambda = 20.f) {
+// kPathTc2: W = 32 and R in {32,48,64,80} (pair_fwd2 / pair_bwd2); kPathTc3: any other d = 256 shape the streaming
+// large-shape kernel tiles (R up to 288 at W <= 64, W <= 128: config 5, the shipped R = 30 / 240 x W = 99 shapes)
+static int shape_path(int R, int W, int d, bool train) {
+  if (tc_supported(R, W, d)) return kPathTc2;
+  if ((!train || kTc3Train) && shape3(R, W, d, nullptr)) return kPathTc3;
+  return kPathGeneric;
+}
+
+static int pick_path(int impl, int R, int W, int d, bool train, int* path, float lambda = 20.f) {
   if (impl == DVLP_IMPL_AUTO) impl = g_default_impl.load();
-  if (impl == DVLP_IMPL_GENERIC) { *tc = false; return DVLP_OK; }
-  bool ok = tc_supported(R, W, d);
+  if (impl == DVLP_IMPL_GENERIC) { *path = kPathGeneric; return DVLP_OK; }
+  if (impl != DVLP_IMPL_AUTO && impl != DVLP_IMPL_TCGEN05) return DVLP_ERR_BAD_ARG;
+  int p = shape_path(R, W, d, train);
   if (!(lambda > 0.f && lambda <= kMaxLambdaTc)) {
     if (impl == DVLP_IMPL_TCGEN05) return DVLP_ERR_BAD_ARG;
-    ok = false;
+    p = kPathGeneric;
   }
-  if (impl == DVLP_IMPL_TCGEN05 && !ok) return DVLP_ERR_BAD_SHAPE;
-  if (impl != DVLP_IMPL_AUTO && impl != DVLP_IMPL_TCGEN05) return DVLP_ERR_BAD_ARG;
-  *tc = ok;
+  if (impl == DVLP_IMPL_TCGEN05 && p == kPathGeneric) return DVLP_ERR_BAD_SHAPE;
+  *path = p;
   return DVLP_OK;
 }
 
@@ -175,7 +200,8 @@ const char* dvlp_error_string(int code) {
 }
 
 int dvlp_last_cuda_error(void) { return g_last_cuda_error; }
-int dvlp_rw_tcgen05_supported(int R, int W, int d) { return tc_supported(R, W, d) ? 1 : 0; }
+int dvlp_rw_tcgen05_supported(int R, int W, int d) { return shape_path(R, W, d, true) != kPathGeneric ? 1 : 0; }
+int dvlp_rw_path(int R, int W, int d, int train) { return shape_path(R, W, d, train != 0); }
 void dvlp_set_default_impl(int impl) { g_default_impl.store(impl); }
 uint64_t dvlp_launch_count(void) { return g_launches.load(); }
 
@@ -203,9 +229,9 @@ int dvlp_profile_read(double* ms, int* counts) {
 
 static size_t workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl, bool train) {
   if (Bv <= 0 || Bt <= 0 || R <= 0 || W <= 0 || d <= 0) return 0;
-  bool tc = false;
-  if (pick_tc(impl, R, W, d, &tc) != DVLP_OK) return 0;
-  return make_workspace(Bv, Bt, R, W, d, in_dtype, tc, train).total;
+  int path = kPathGeneric;
+  if (pick_path(impl, R, W, d, train, &path) != DVLP_OK) return 0;
+  return make_workspace(Bv, Bt, R, W, d, in_dtype, path, train).total;
 }
 size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl) {
   return workspace_bytes(Bv, Bt, R, W, d, in_dtype, impl, true);
@@ -220,22 +246,28 @@ static int scores_fwd(const void* im, const void* s, const float* im_mask, const
   int rc = check_common(im, s, im_mask, s_mask, Bv, Bt, R, W, d, in_dtype);
   if (rc) return rc;
   if (!scores) return DVLP_ERR_NULL_POINTER;
-  bool tc = false;
-  if ((rc = pick_tc(impl, R, W, d, &tc, lambda))) return rc;
+  int path = kPathGeneric;
+  if ((rc = pick_path(impl, R, W, d, train, &path, lambda))) return rc;
   if ((rc = device_ok())) return rc;
-  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc, train);
+  const bool tc = path != kPathGeneric;
+  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, path, train);
   if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
   if ((uintptr_t)workspace & 255) return DVLP_ERR_MISALIGNED;
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope p(kProfPrep, st);
-    if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, false, ws, L, st))) return rc;
+    if (path == kPathTc3) {
+      if ((rc = run_prep3(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, ws, L, st))) return rc;
+    } else if ((rc = run_prep(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, tc, false, ws, L, st))) {
+      return rc;
+    }
   }
   ProfScope p(kProfFwd, st);
   if (tc) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
+    if (path == kPathTc3) return run_pair_fwd3(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, train, st);
     return run_pair_fwd2(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, train, st);
   }
   PairArgs a{};
@@ -270,10 +302,11 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   if (rc) return rc;
   if (!d_scores || !d_im || !d_s) return DVLP_ERR_NULL_POINTER;
   if (out_dtype != DVLP_F32 && out_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
-  bool tc = false;
-  if ((rc = pick_tc(impl, R, W, d, &tc, lambda))) return rc;
+  int path = kPathGeneric;
+  if ((rc = pick_path(impl, R, W, d, true, &path, lambda))) return rc;
   if ((rc = device_ok())) return rc;
-  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, tc, true);
+  const bool tc = path != kPathGeneric;
+  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, path, true);
   if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
@@ -384,8 +417,8 @@ int dvlp_ranks_v2t(const double* sims, int Nq, int Nv, double* ranks, void* stre
 int dvlp_rw_bwd_out_dtype_supported(int impl, int R, int W, int d, float lambda, int out_dtype) {
   if (out_dtype == DVLP_F32) return 1;
   if (out_dtype != DVLP_BF16) return 0;
-  bool tc = false;
-  if (pick_tc(impl, R, W, d, &tc, lambda) != DVLP_OK || !tc) return 0;
+  int path = kPathGeneric;
+  if (pick_path(impl, R, W, d, true, &path, lambda) != DVLP_OK || path == kPathGeneric) return 0;
   return (d == 256 && (R % 16) == 0 && (W % 16) == 0 && R <= 128 && W <= 128) ? 1 : 0;   // run_grad_finalize_tc
 }
 

@@ -106,13 +106,24 @@ struct Workspace {
   size_t rowv, colv;         // tcgen05: per-unit query scalars saved by the forward for pair_bwd2.cu: float4 (units,128) =
                              // (nB, thr1, 1/|c1|, cos1) per word, float4 (units,4,R) = (nA, thr2, 1/|c2|, cos2) per (text, region)
   size_t gbd;                // tcgen05: block-diagonal bf16 text Gram tiles (ceil(Bt/4), 128, 128)
+  // large-shape tcgen05 kernels (pair_fwd3.cu): padded per-region / per-tile-row vectors and Gram tiles
+  size_t alpha3, m2v3;       // fp32 (Bv, Rp): inverse norms (0 beyond R), log2-domain mask terms (-1e30 beyond R)
+  size_t beta3, m2t3;        // fp32 (tiles, 128) in tile-row order (text slot * WP + word)
+  size_t gbd3;               // bf16 (tiles, 128, 128) block-diagonal text Gram tiles for TPT texts of WP padded words
   size_t scratch;            // generic kernels: per-CTA pair scratch
   size_t total;
   int n_cta;                 // generic kernels: persistent grid size
   size_t scratch_per_cta;    // floats
 };
 
-Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, bool tc, bool train = true);
+// which pair kernels serve a call
+enum Path { kPathGeneric = 0, kPathTc2 = 2, kPathTc3 = 3 };   // fp32 CUDA cores; pair_fwd2/bwd2 (W = 32, R <= 80); pair_fwd3
+
+// tiling of the large-shape kernels (pair_fwd3.cu: shape3)
+struct Shape3 { int NB, NQ, WP, TPT, Rp, nch; };
+bool shape3(int R, int W, int d, Shape3* s);
+
+Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int path, bool train = true);
 
 // arguments of the generic pair kernels
 struct PairArgs {

@@ -346,4 +346,92 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
   return DVLP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Prologue of the large-shape tcgen05 kernels (pair_fwd3.cu): the per-row / per-item quantities above (inverse norms,
+// log2-domain mask terms, bf16 text Gram matrices) re-laid out for its padded tiles:
+//   alpha3 / m2v3 [Bv][Rp]        regions >= R: alpha 0, mask term -1e30 (their exponentials are exact zeros)
+//   beta3 / m2t3  [tiles][128]    tile row = text slot * WP + word; padded words and absent texts: 0 / -1e30
+//   gbd3          [tiles][128][128] bf16: the TPT text Gram matrices of a tile on the diagonal, zeros elsewhere
+__global__ void __launch_bounds__(256) k_pack3(const float* __restrict__ alpha, const float* __restrict__ m2v,
+                                               const float* __restrict__ beta, const float* __restrict__ m2t,
+                                               const __nv_bfloat16* __restrict__ gtb, int Bv, int Bt, int R, int W, int Rp,
+                                               int WP, int TPT, int tiles, float* __restrict__ alpha3,
+                                               float* __restrict__ m2v3, float* __restrict__ beta3,
+                                               float* __restrict__ m2t3, __nv_bfloat16* __restrict__ gbd3) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t e = t0; e < (size_t)Bv * Rp; e += stride) {
+    const int i = (int)(e / Rp), r = (int)(e - (size_t)i * Rp);
+    const bool ok = r < R;
+    alpha3[e] = ok ? alpha[(size_t)i * R + r] : 0.f;
+    m2v3[e] = ok ? m2v[(size_t)i * R + r] : -1e30f;
+  }
+  for (size_t e = t0; e < (size_t)tiles * 128; e += stride) {
+    const int row = (int)(e & 127), tile = (int)(e >> 7);
+    const int ts = row / WP, w = row - ts * WP, j = tile * TPT + ts;
+    const bool ok = j < Bt && w < W;
+    beta3[e] = ok ? beta[(size_t)j * W + w] : 0.f;
+    m2t3[e] = ok ? m2t[(size_t)j * W + w] : -1e30f;
+  }
+  for (size_t e = t0; e < (size_t)tiles * 128 * 64; e += stride) {       // two bf16 columns per thread
+    const int col = (int)(e & 63) * 2, row = (int)((e >> 6) & 127), tile = (int)(e >> 13);
+    const int ts = row / WP, w = row - ts * WP, j = tile * TPT + ts;
+    float v[2] = {0.f, 0.f};
+    if (j < Bt && w < W) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = col + h, cs = c / WP, w2 = c - cs * WP;
+        if (cs == ts && w2 < W) v[h] = __bfloat162float(gtb[((size_t)j * W + w) * W + w2]);
+      }
+    }
+    reinterpret_cast<__nv_bfloat162*>(gbd3)[e] = __floats2bfloat162_rn(v[0], v[1]);
+  }
+}
+
+int run_prep3(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt, int R, int W,
+              int d, float lambda, int in_dtype, char* ws, const Workspace& L, cudaStream_t st) {
+  Shape3 s3;
+  if (!shape3(R, W, d, &s3)) return DVLP_ERR_BAD_SHAPE;
+  const __nv_bfloat16* vb = (const __nv_bfloat16*)im;
+  const __nv_bfloat16* tb = (const __nv_bfloat16*)s;
+  if (in_dtype == DVLP_F32) {      // "bf16 in": every later stage sees exactly the operands the tensor cores see
+    size_t nv = (size_t)Bv * R * d, nt = (size_t)Bt * W * d;
+    k_to_bf16<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>((const float*)im, nv, (__nv_bfloat16*)(ws + L.vb));
+    DVLP_LAUNCH_OK();
+    k_to_bf16<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>((const float*)s, nt, (__nv_bfloat16*)(ws + L.tb));
+    DVLP_LAUNCH_OK();
+    vb = (const __nv_bfloat16*)(ws + L.vb);
+    tb = (const __nv_bfloat16*)(ws + L.tb);
+  }
+  float* alpha = (float*)(ws + L.alpha);
+  float* beta = (float*)(ws + L.beta);
+  k_prep_rows<__nv_bfloat16><<<(Bv * R + 7) / 8, 256, 0, st>>>(vb, Bv * R, d, alpha, nullptr, nullptr);
+  DVLP_LAUNCH_OK();
+  k_prep_rows<__nv_bfloat16><<<(Bt * W + 7) / 8, 256, 0, st>>>(tb, Bt * W, d, beta, nullptr, nullptr);
+  DVLP_LAUNCH_OK();
+  k_mask_terms<<<(Bv + 7) / 8, 256, 0, st>>>(im_mask, Bv, R, lambda, (float*)(ws + L.mterm_v), (float*)(ws + L.m2v));
+  DVLP_LAUNCH_OK();
+  k_mask_terms<<<(Bt + 7) / 8, 256, 0, st>>>(s_mask, Bt, W, lambda, (float*)(ws + L.mterm_t), (float*)(ws + L.m2t));
+  DVLP_LAUNCH_OK();
+  {
+    const size_t smem = (size_t)W * (d + 1) * 4;
+    static DeviceOnce attr_once;
+    if (attr_once.pending()) {
+      DVLP_CUDA_OK(cudaFuncSetAttribute(k_gram_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_once.done();
+    }
+    k_gram_tile<<<Bt, 256, smem, st>>>(tb, beta, W, d, nullptr, (__nv_bfloat16*)(ws + L.gtb));
+    DVLP_LAUNCH_OK();
+  }
+  const int tiles = (Bt + s3.TPT - 1) / s3.TPT;
+  const size_t work = (size_t)tiles * 128 * 64;
+  int grid = (int)((work + 256 * 4 - 1) / (256 * 4));
+  grid = grid < 1 ? 1 : (grid > 148 * 8 ? 148 * 8 : grid);
+  k_pack3<<<grid, 256, 0, st>>>(alpha, (const float*)(ws + L.m2v), beta, (const float*)(ws + L.m2t),
+                                (const __nv_bfloat16*)(ws + L.gtb), Bv, Bt, R, W, s3.Rp, s3.WP, s3.TPT, tiles,
+                                (float*)(ws + L.alpha3), (float*)(ws + L.m2v3), (float*)(ws + L.beta3),
+                                (float*)(ws + L.m2t3), (__nv_bfloat16*)(ws + L.gbd3));
+  DVLP_LAUNCH_OK();
+  return DVLP_OK;
+}
+
 }  // namespace dvlp

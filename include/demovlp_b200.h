@@ -53,6 +53,10 @@ const char* dvlp_error_string(int code);
 int dvlp_last_cuda_error(void);
 /* 1 when dvlp_rw_scores_* would take the tcgen05 path for this shape. */
 int dvlp_rw_tcgen05_supported(int R, int W, int d);
+/* which pair kernels DVLP_IMPL_AUTO selects for a shape: 0 = generic fp32 CUDA cores, 2 = tcgen05 small-shape kernels
+ * (W = 32, R in {32,48,64,80}), 3 = tcgen05 large-shape streaming kernel (any R, W <= 128 it can tile: R = 288 x W = 64,
+ * the reference's shipped R = 30 / 240 x W = 99, ...).  train = 0: forward-only calls (dvlp_rw_scores_infer). */
+int dvlp_rw_path(int R, int W, int d, int train);
 /* process-wide default for `impl` arguments given as DVLP_IMPL_AUTO. */
 void dvlp_set_default_impl(int impl);
 /* 1 when dvlp_rw_scores_bwd can write its gradients in `out_dtype` for this impl / shape / lambda
