@@ -37,6 +37,10 @@ int run_prep(const void*, const void*, const float*, const float*, int, int, int
              const Workspace&, cudaStream_t);
 int run_prep3(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, char*,
               const Workspace&, cudaStream_t);
+int run_pair_bwd3(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
+                  const float* d_scores, char* ws, const Workspace& L, cudaStream_t st);
+int run_grad_gemm3(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
+                   const Workspace& L, cudaStream_t st);
 int run_pair_fwd3(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
                   float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
 int run_pair_generic(bool backward, const PairArgs& a, int n_cta, cudaStream_t st);
@@ -96,7 +100,17 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int 
   L.dth = take(train ? nt * d * 4 : 0);
   L.dgv = take(train ? nv * R * 4 : 0);
   L.dgt = take(train ? nt * W * 4 : 0);
-  {
+  if (tc3 && train) {          // (directly behind dgt: one memset clears every accumulator of the backward)
+    Shape3 s3{};
+    shape3(R, W, d, &s3);
+    const size_t tiles = (size_t)(Bt + s3.TPT - 1) / s3.TPT, units = tiles * Bv;
+    L.dgt3 = take(tiles * 128 * 128 * 4);
+    L.pa = take(units * 128 * s3.Rp * 2);
+    L.ud1 = take(units * 128 * s3.Rp * 2);
+    L.cb = take(units * 128 * 256 * 2);
+    L.rowv = take(units * 128 * 16);
+    L.colv = take(units * s3.TPT * s3.Rp * 16);
+  } else {
     const size_t units = (size_t)Bv * ((Bt + 3) / 4);
     L.pa = take(tc2 && train ? units * R * 128 * 2 : 0);
     L.rowv = take(tc2 && train ? units * 128 * 16 : 0);
@@ -138,7 +152,7 @@ static int check_common(const void* im, const void* s, const float* im_mask, con
 // softmax would not), so such calls go to the generic kernels (auto) or are refused (explicit tcgen05).
 constexpr float kMaxLambdaTc = 40.f;
 // the large-shape kernels (pair_fwd3.cu) serve the forward; their backward partner is selected here once it exists
-constexpr bool kTc3Train = false;
+constexpr bool kTc3Train = true;
 
 // kPathTc2: W = 32 and R in {32,48,64,80} (pair_fwd2 / pair_bwd2); kPathTc3: any other d = 256 shape the streaming
 // large-shape kernel tiles (R up to 288 at W <= 64, W <= 128: config 5, the shipped R = 30 / 240 x W = 99 shapes)
@@ -310,11 +324,35 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
-  // zero the accumulators (one contiguous range: dvh .. dgt; the tcgen05 dV' GEMM overwrites dvh, so it starts at dth)
-  DVLP_CUDA_OK(cudaMemsetAsync(ws + (tc ? L.dth : L.dvh), 0, L.pa - (tc ? L.dth : L.dvh), st));
+  // zero the accumulators (one contiguous range: dvh .. dgt [.. dgt3]; the tcgen05 small-shape dV' GEMM overwrites dvh,
+  // so it starts at dth)
+  {
+    const size_t z0 = path == kPathTc2 ? L.dth : L.dvh;
+    DVLP_CUDA_OK(cudaMemsetAsync(ws + z0, 0, L.pa - z0, st));
+  }
+  if (path == kPathTc3) {
+    const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
+    const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
+    if (out_dtype != DVLP_F32) return DVLP_ERR_BAD_DTYPE;
+    {
+      ProfScope pb(kProfBwd, st);
+      if ((rc = run_pair_bwd3(vb, tb, Bv, Bt, R, W, d, lambda, d_scores, ws, L, st))) return rc;
+    }
+    {
+      ProfScope pg(kProfGG, st);
+      if ((rc = run_grad_gemm3(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
+    }
+    // l2-norm backward of the raw rows; the video side has no Gram term in the direct form (dgv stays zero)
+    ProfScope pf(kProfFinal, st);
+    if ((rc = run_grad_finalize(vb, DVLP_BF16, (const float*)(ws + L.alpha), (const float*)(ws + L.dvh),
+                                (const float*)(ws + L.dgv), Bv, R, d, 1, (float*)d_im, st)))
+      return rc;
+    return run_grad_finalize(tb, DVLP_BF16, (const float*)(ws + L.beta), (const float*)(ws + L.dth),
+                             (const float*)(ws + L.dgt), Bt, W, d, 1, (float*)d_s, st);
+  }
   int prescaled = 0, dgt_swz = 0;
   {
-  if (tc) {
+  if (path == kPathTc2) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
     {
@@ -418,7 +456,7 @@ int dvlp_rw_bwd_out_dtype_supported(int impl, int R, int W, int d, float lambda,
   if (out_dtype == DVLP_F32) return 1;
   if (out_dtype != DVLP_BF16) return 0;
   int path = kPathGeneric;
-  if (pick_path(impl, R, W, d, true, &path, lambda) != DVLP_OK || path == kPathGeneric) return 0;
+  if (pick_path(impl, R, W, d, true, &path, lambda) != DVLP_OK || path != kPathTc2) return 0;
   return (d == 256 && (R % 16) == 0 && (W % 16) == 0 && R <= 128 && W <= 128) ? 1 : 0;   // run_grad_finalize_tc
 }
 

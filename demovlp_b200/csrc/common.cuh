@@ -110,6 +110,8 @@ struct Workspace {
   size_t alpha3, m2v3;       // fp32 (Bv, Rp): inverse norms (0 beyond R), log2-domain mask terms (-1e30 beyond R)
   size_t beta3, m2t3;        // fp32 (tiles, 128) in tile-row order (text slot * WP + word)
   size_t gbd3;               // bf16 (tiles, 128, 128) block-diagonal text Gram tiles for TPT texts of WP padded words
+  size_t dgt3;               // fp32 (tiles, 128, 128) text Gram gradients per tile (pair_bwd3.cu), unpacked into dgt
+  size_t ud1, cb;            // bf16 spills of pair_bwd3.cu: UD1 (units, 128, Rp), C_bf16 (units, 128, 256); P uses `pa`
   size_t scratch;            // generic kernels: per-CTA pair scratch
   size_t total;
   int n_cta;                 // generic kernels: persistent grid size
