@@ -533,7 +533,7 @@ def run_ours(args):
         rn.sync()
         sampler = ClockSampler(local_rank) if (headline and rank == 0) else None
         dev_ms, wall, launches = rn.timed(flush, sampler)
-        res = {"runner": rn, "dev_ms": dev_ms, "wall": wall, "launches": launches, "sampler": sampler,
+        res = {"runner": rn, "dev_ms": dev_ms, "wall": wall, "launches": launches, "sampler": sampler, "graph": bool(rn.gsteps),
                "value": rn.B * rn.B * args.steps / (dev_ms * 1e-3)}
         res["e2e"], res["d2h"] = rn.e2e(False)
         if headline:
@@ -609,7 +609,7 @@ def run_ours(args):
             "run": {"per_gpu_batch": b_loc,
                     "parallelism": f"video-row sharding x{world}" if world > 1 else "single GPU",
                     "transport": transport, "kernel_path": "tcgen05" if tc else "generic fp32 CUDA cores",
-                    "wall_ms_per_step_incl_flush": head["wall"] / args.steps * 1e3, "cuda_graph": bool(rn.gsteps),
+                    "wall_ms_per_step_incl_flush": head["wall"] / args.steps * 1e3, "cuda_graph": head["graph"],
                     "e2e_pipeline": "H2D of step k+1 on a copy stream under step k; host waits for each step's results"},
             "e2e": {"value": head["e2e"], "unit": UNIT, "h2d_bytes_per_step": rn.h2d, "d2h_bytes_per_step": head["d2h"],
                     "returns": "loss triple only: the gradients stay on the GPU, as for a loss consumed by a GPU trainer "

@@ -342,10 +342,10 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
       ProfScope pg(kProfGG, st);
       if ((rc = run_grad_gemm3(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
     }
-    // l2-norm backward of the raw rows; the video side has no Gram term in the direct form (dgv stays zero)
+    // l2-norm backward of the raw rows; the video side has no Gram term in the direct form
     ProfScope pf(kProfFinal, st);
-    if ((rc = run_grad_finalize(vb, DVLP_BF16, (const float*)(ws + L.alpha), (const float*)(ws + L.dvh),
-                                (const float*)(ws + L.dgv), Bv, R, d, 1, (float*)d_im, st)))
+    if ((rc = run_grad_finalize(vb, DVLP_BF16, (const float*)(ws + L.alpha), (const float*)(ws + L.dvh), nullptr, Bv, R, d, 1,
+                                (float*)d_im, st)))
       return rc;
     return run_grad_finalize(tb, DVLP_BF16, (const float*)(ws + L.beta), (const float*)(ws + L.dth),
                              (const float*)(ws + L.dgt), Bt, W, d, 1, (float*)d_s, st);

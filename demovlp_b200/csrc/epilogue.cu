@@ -260,8 +260,34 @@ int run_grad_finalize_tc(const void* v, const void* t, const float* alpha, const
   return DVLP_OK;
 }
 
+// No Gram term (the direct-form video side of pair_bwd3.cu): the plain l2-norm backward, one warp per row.
+template <typename Tin>
+__global__ void __launch_bounds__(256) k_l2norm_bwd_rows(const Tin* __restrict__ x, const float* __restrict__ inv,
+                                                         const float* __restrict__ dxh, int rows, int d, int prescaled,
+                                                         float* __restrict__ d_x) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float a = inv[row];
+  const float gsc = prescaled ? 1.f / a : 1.f;
+  const Tin* xr = x + (size_t)row * d;
+  const float* gr = dxh + (size_t)row * d;
+  float dot = 0.f;
+  for (int k = lane; k < d; k += 32) dot = fmaf(to_f32(xr[k]) * a, gr[k] * gsc, dot);
+  dot = warp_sum(dot);
+  for (int k = lane; k < d; k += 32) d_x[(size_t)row * d + k] = a * (gr[k] * gsc - to_f32(xr[k]) * a * dot);
+}
+
 int run_grad_finalize(const void* x, int in_dtype, const float* inv, const float* dxh, const float* dG, int items,
                       int L, int d, int prescaled, float* d_x, cudaStream_t st) {
+  if (!dG) {
+    const int rows = items * L;
+    if (in_dtype == DVLP_BF16)
+      k_l2norm_bwd_rows<__nv_bfloat16><<<(rows + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)x, inv, dxh, rows, d, prescaled, d_x);
+    else
+      k_l2norm_bwd_rows<float><<<(rows + 7) / 8, 256, 0, st>>>((const float*)x, inv, dxh, rows, d, prescaled, d_x);
+    DVLP_LAUNCH_OK();
+    return DVLP_OK;
+  }
   const size_t smem = ((size_t)L * 16 + 16 * 8 + 16) * 4;
   if (d <= 256 && smem <= 48 * 1024) {
     if (in_dtype == DVLP_BF16)

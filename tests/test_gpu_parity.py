@@ -17,7 +17,7 @@ GRAD_TOL = 1e-2       # north star: gradients within 1e-2 relative
 IMPLS = ["generic", "auto"]
 
 
-MAX_RANK_FLIPS_96 = 10    # end-to-end t2v rank flips tolerated on the 96 x 96 eval fixture (count is recorded)
+MAX_RANK_FLIPS_96 = 3     # end-to-end t2v rank flips tolerated on the 96 x 96 eval fixture (count is recorded)
 
 
 def dev(b):
@@ -426,3 +426,137 @@ def test_validation_feed_matches_segmented_eval():
     assert got.dtype == np.float64 and got.shape == (40, 40)
     assert np.array_equal(got, want)
     assert M.t2v_metrics(got) == M.t2v_metrics(want)
+
+
+LARGE_SHAPES = [(288, 64), (240, 99), (30, 99)]     # config 5 and the reference's shipped fine-tune / pre-train shapes
+
+
+def test_large_shapes_are_served_by_tcgen05():
+    """dvlp_rw_tcgen05_supported is true for (288, 64), (240, 99), (30, 99) -- forward AND backward."""
+    lib = _lib.load()
+    for R, W in LARGE_SHAPES + [(80, 32), (17, 9), (130, 128)]:
+        assert lib.dvlp_rw_tcgen05_supported(R, W, 256) == 1, (R, W)
+        assert lib.dvlp_rw_path(R, W, 256, 1) in (2, 3) and lib.dvlp_rw_path(R, W, 256, 0) in (2, 3)
+    assert lib.dvlp_rw_path(80, 32, 256, 1) == 2 and lib.dvlp_rw_path(288, 64, 256, 1) == 3
+    assert lib.dvlp_rw_tcgen05_supported(80, 32, 128) == 0          # d != 256: generic kernels
+    assert lib.dvlp_rw_tcgen05_supported(80, 200, 256) == 0         # more than 128 words: generic kernels
+
+
+@pytest.mark.parametrize("name", ["didemo_small", "ft_ragged", "pt_r30"])
+def test_large_shape_fixtures_under_explicit_tcgen05(name):
+    """Reference-minted fixtures of the config-5 / real shapes through impl="tcgen05" (pair_fwd3 / pair_bwd3 /
+    grad_gemm3): loss triple 2e-3 absolute, every gradient 1e-2 relative."""
+    g = load_golden("loss_" + name)
+    b, focal = batch_for(g)
+    d = dev(b)
+    im = d.im.to(torch.bfloat16).requires_grad_(True)
+    s = d.s.to(torch.bfloat16).requires_grad_(True)
+    gt = d.g_text.clone().requires_grad_(True)
+    gv = d.g_vid.clone().requires_grad_(True)
+    mod = L.GlobalLocalLoss(focal_type=focal, coef=1.0).to("cuda")
+    mod.local_loss.impl = "tcgen05"
+    loss, gl, ll = mod(L.sim_matrix(gt, gv), im, s, d.im_mask, d.s_len, d.s_mask)
+    loss.backward()
+    got = np.array([loss.item(), gl.item(), ll.item()])
+    assert np.abs(got - g["losses"]).max() < SCORE_TOL, (got, g["losses"])
+    sc = ops.rw_scores(d.im.to(torch.bfloat16), d.s.to(torch.bfloat16), d.im_mask, d.s_mask,
+                       focal_equal=(focal == "equal"), impl="tcgen05")
+    assert np.abs(sc.cpu().numpy() - g["scores"]).max() < SCORE_TOL
+    assert rel_err(im.grad.float().cpu(), g["d_im"]) < GRAD_TOL
+    assert rel_err(s.grad.float().cpu(), g["d_s"]) < GRAD_TOL
+    _record("large_shape_fixture", dict(case=name, loss_abs_err=float(np.abs(got - g["losses"]).max()),
+                                        d_im_rel=rel_err(im.grad.float().cpu(), g["d_im"]),
+                                        d_s_rel=rel_err(s.grad.float().cpu(), g["d_s"])))
+
+
+@pytest.mark.parametrize("shape", [(5, 288, 64, 7), (3, 240, 99, 4), (6, 30, 99, 9), (4, 100, 20, 6), (7, 48, 64, 5),
+                                   (3, 130, 128, 3), (2, 17, 9, 3)])
+def test_large_shape_kernel_ragged_counts_vs_oracle(shape):
+    """pair_fwd3 / pair_bwd3 for ragged video / text counts, padded regions (R not a multiple of the chunk), padded
+    words (W < 32 / 64 / 128) and both focal types, against the oracle's autograd on the same bf16-rounded inputs."""
+    Bv, R, W, Bt = shape
+    b = synth.make_batch(max(Bv, Bt), R, W, 256, seed=43)
+    im, s = b.im[:Bv].to(torch.bfloat16), b.s[:Bt].to(torch.bfloat16)
+    imm, sm = b.im_mask[:Bv].contiguous(), b.s_mask[:Bt].contiguous()
+    w = torch.randn(Bv, Bt, generator=torch.Generator().manual_seed(5))
+    for focal in ("equal", "prob"):
+        ic = im.float().clone().requires_grad_(True)
+        sc = s.float().clone().requires_grad_(True)
+        want = O.pair_scores(ic, sc, imm, sm, focal=focal)
+        (want * w).sum().backward()
+        x = im.cuda().requires_grad_(True)
+        y = s.cuda().requires_grad_(True)
+        got = ops.rw_scores(x, y, imm.cuda(), sm.cuda(), focal_equal=(focal == "equal"), impl="tcgen05")
+        (got * w.cuda()).sum().backward()
+        assert (got.detach().cpu() - want.detach()).abs().max() < SCORE_TOL
+        assert torch.isfinite(x.grad).all() and torch.isfinite(y.grad).all()
+        assert rel_err(x.grad.float().cpu(), ic.grad) < GRAD_TOL
+        assert rel_err(y.grad.float().cpu(), sc.grad) < GRAD_TOL
+
+
+def test_config5_rank_share_vs_oracle():
+    """One rank's share of BASELINE config 5 at FULL size (64 videos x all 512 texts, R = 288, W = 64) through the
+    tcgen05 large-shape kernels, against the oracle evaluated in 4-row blocks: score rows, the row-local RWALoss
+    partial, d_im of the shard and the partial d_s of all texts (what the reduce-scatter would sum)."""
+    Bt, bv, R, W = 512, 64, 288, 64
+    b = synth.make_config("c5")
+    im_c = b.im[:bv].clone().requires_grad_(True)
+    s_c = b.s.clone().requires_grad_(True)
+    total, rows = 0.0, []
+    for lo in range(0, bv, 4):
+        sc = O.pair_scores(im_c[lo:lo + 4], s_c, b.im_mask[lo:lo + 4], b.s_mask, focal="equal")
+        rows.append(sc.detach())
+        logp = torch.log_softmax(sc * 20.0, dim=1)
+        tgt = torch.zeros_like(sc)
+        tgt[torch.arange(4), torch.arange(lo, lo + 4)] = 1.0
+        part = (logp.exp() * (logp - torch.log(tgt + 1e-6))).sum() / Bt
+        part.backward()
+        total += part.item()
+    d = dev(b)
+    im, s = d.im[:bv].to(torch.bfloat16).contiguous(), d.s.to(torch.bfloat16)
+    scores, state = ops.rw_scores_fwd_raw(im, s, d.im_mask[:bv].contiguous(), d.s_mask, 20.0, 1, "tcgen05")
+    part, d_scores = ops.rwa_tail_raw(scores, 20.0, 0, Bt)
+    d_im, d_s = ops.rw_scores_bwd_raw(state, d_scores)
+    assert (scores.cpu() - torch.cat(rows)).abs().max() < SCORE_TOL
+    assert abs(part.item() - total) < SCORE_TOL
+    e_im, e_s = rel_err(d_im.float().cpu(), im_c.grad), rel_err(d_s.float().cpu(), s_c.grad)
+    _record("config5_rank_share", dict(score_abs_err=float((scores.cpu() - torch.cat(rows)).abs().max()),
+                                       loss_abs_err=abs(part.item() - total), d_im_rel=e_im, d_s_rel=e_s))
+    assert e_im < GRAD_TOL and e_s < GRAD_TOL
+
+
+@pytest.mark.parametrize("shape", [(80, 32), (240, 99)])
+def test_eval_1000_end_to_end_vs_reference_matrix(shape):
+    """BASELINE config 4 at FULL size: the 1000 x 1000 region-word matrix + sim_matrix (orientation quirk of
+    trainer/trainer_dist.py:369-385 kept) against the matrix the unmodified reference builds with get_sim_by_segment
+    (oracle/make_golden_eval1000.py), at the synthetic shape and at the shipped fine-tune shape R = 240, W = 99.
+    The rank kernel is bit-exact on the reference matrix; end-to-end rank differences are counted and recorded."""
+    import os
+    R, W = shape
+    path = os.path.join(os.path.dirname(__file__), "golden", f"eval_1000_r{R}_w{W}.npz")
+    if not os.path.isfile(path):
+        pytest.skip("fixture missing (python oracle/make_golden_eval1000.py)")
+    e = np.load(path)
+    b = synth.make_batch(1000, R, W, 256, seed=3, kappa=0.12)
+    assert abs(float(b.im.double().sum()) - e["checksum"][0]) < 1e-6
+    ref_full = e["gsim"].astype(np.float64) + e["local"].astype(np.float64)       # exact: both addends are float32
+    np.testing.assert_array_equal(M.t2v_ranks(ref_full), e["t2v_ranks"])             # rank kernel on the reference matrix
+    keys = [str(k) for k in e["keys"]]
+    got_ref = M.t2v_metrics(ref_full)
+    for k, v in zip(keys, e["t2v"]):
+        assert got_ref[k] == pytest.approx(float(v), rel=1e-12, abs=1e-12)
+    mod = L.RWALoss(focal_type="equal")
+    local = mod.get_sim_by_segment(b.im.to(torch.bfloat16), b.s.to(torch.bfloat16), b.im_mask, b.s_len, b.s_mask, device="cuda")
+    assert local.dtype == np.float64 and local.shape == (1000, 1000)
+    err = float(np.abs(local - e["local"]).max())
+    assert err < SCORE_TOL
+    full = L.sim_matrix(b.g_text.cuda(), b.g_vid.cuda()).double().cpu().numpy() + local
+    ranks = M.t2v_ranks(full)
+    mism = int((ranks != e["t2v_ranks"]).sum())
+    got = M.t2v_metrics(full)
+    ref = dict(zip(keys, (float(v) for v in e["t2v"])))
+    _record("eval_rank_mismatch", dict(case=f"eval_1000_r{R}_w{W}", impl="auto", mismatches=mism, rows=1000,
+                                       max_abs_rank_diff=int(np.abs(ranks - e["t2v_ranks"]).max()), max_abs_score_err=err,
+                                       R1=got["R1"], R1_ref=ref["R1"], MeanR=got["MeanR"], MeanR_ref=ref["MeanR"]))
+    assert mism <= 80                              # 8 %: score noise 1e-4 against row gaps of ~5e-4 (SURVEY 7.4-6)
+    assert abs(got["MeanR"] - ref["MeanR"]) < 0.5 and abs(got["R1"] - ref["R1"]) <= 0.5
