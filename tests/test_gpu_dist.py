@@ -114,7 +114,9 @@ def test_peer_memory_transport_matches_nccl():
     for o in outs:
         a, c = o["p2p"], o["nccl"]
         assert abs(a["loss"].item() - c["loss"].item()) < 1e-6 * max(1, abs(c["loss"].item()))
-        assert torch.equal(a["d_im"], c["d_im"])                    # same kernels, same inputs
+        # same kernels, same inputs -- up to the order of the fp32 red.global adds of the video Gram gradients when
+        # the tiles of a video are walked by several CTAs (not bit-reproducible run to run)
+        assert rel_err(a["d_im"], c["d_im"]) < 1e-4
         assert rel_err(a["d_s"], c["d_s"]) < 4e-3                   # one bf16 rounding, sums in a different order
         assert torch.equal(a["d_gt"], c["d_gt"]) and torch.equal(a["d_gv"], c["d_gv"])
     # every rank got the same loss bits from the rank-ordered scalar sum
