@@ -35,6 +35,8 @@ SYMBOLS = {
     "dvlp_rw_scores_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p, _p, _sz, _p]),
     "dvlp_rw_infer_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "dvlp_rw_scores_infer": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p, _p, _sz, _p]),
+    "dvlp_rw_grouped_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "dvlp_rw_scores_grouped_infer": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _sz, _p]),
     "dvlp_rw_scores_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p, _p, _p, _i, _p, _sz, _p]),
     "dvlp_rwa_loss_fwd_bwd": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p]),
     "dvlp_sim_matrix_fwd": (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _p, _p]),

@@ -36,13 +36,13 @@ ProfScope::~ProfScope() {
 int run_prep(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, bool, bool, char*,
              const Workspace&, cudaStream_t);
 int run_prep3(const void*, const void*, const float*, const float*, int, int, int, int, int, float, int, char*,
-              const Workspace&, cudaStream_t);
+              const Workspace&, cudaStream_t, int n_t = 0);
 int run_pair_bwd3(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
                   const float* d_scores, char* ws, const Workspace& L, cudaStream_t st);
 int run_grad_gemm3(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
                    const Workspace& L, cudaStream_t st);
 int run_pair_fwd3(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
-                  float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
+                  float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st, int n_t = 0);
 int run_pair_generic(bool backward, const PairArgs& a, int n_cta, cudaStream_t st);
 int run_grad_finalize(const void*, int, const float*, const float*, const float*, int, int, int, int, float*,
                       cudaStream_t);
@@ -71,7 +71,7 @@ void* g_trace_buffer = nullptr;   // set through dvlp_debug_set_trace (tools/tra
 // shapes served by the tcgen05 kernels: d = 256, W = 32 words, R a multiple of 16 in [32, 80]
 bool tc_supported(int R, int W, int d) { return d == 256 && W == 32 && (R == 80 || R == 64 || R == 48 || R == 32); }
 
-Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int path, bool train) {
+Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int path, bool train, int n_t) {
   Workspace L{};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
@@ -120,7 +120,8 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int 
   if (tc3) {
     Shape3 s3{};
     shape3(R, W, d, &s3);
-    const size_t tiles = (size_t)(Bt + s3.TPT - 1) / s3.TPT;
+    // grouped (multiple-choice) calls tile every group's n_t texts separately
+    const size_t tiles = n_t > 0 ? (size_t)Bv * ((n_t + s3.TPT - 1) / s3.TPT) : (size_t)(Bt + s3.TPT - 1) / s3.TPT;
     L.alpha3 = take((size_t)Bv * s3.Rp * 4);
     L.m2v3 = take((size_t)Bv * s3.Rp * 4);
     L.beta3 = take(tiles * 128 * 4);
@@ -306,6 +307,37 @@ int dvlp_rw_scores_infer(const void* im, const void* s, const float* im_mask, co
                          void* workspace, size_t workspace_bytes, void* stream) {
   return scores_fwd(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, focal_equal, in_dtype, impl, scores, workspace,
                     workspace_bytes, stream, false);
+}
+
+size_t dvlp_rw_grouped_workspace_bytes(int n_groups, int n_per_group, int R, int W, int d, int in_dtype) {
+  if (n_groups <= 0 || n_per_group <= 0 || !shape3(R, W, d, nullptr)) return 0;
+  return make_workspace(n_groups, n_groups * n_per_group, R, W, d, in_dtype, kPathTc3, false, n_per_group).total;
+}
+
+int dvlp_rw_scores_grouped_infer(const void* im, const void* s, const float* im_mask, const float* s_mask, int n_groups,
+                                 int n_per_group, int R, int W, int d, float lambda, int focal_equal, int in_dtype,
+                                 float* scores, void* workspace, size_t workspace_bytes, void* stream) {
+  const int Bv = n_groups, Bt = n_groups * n_per_group;
+  if (n_per_group <= 0) return DVLP_ERR_BAD_SHAPE;
+  int rc = check_common(im, s, im_mask, s_mask, Bv, Bt, R, W, d, in_dtype);
+  if (rc) return rc;
+  if (!scores) return DVLP_ERR_NULL_POINTER;
+  if (!shape3(R, W, d, nullptr)) return DVLP_ERR_BAD_SHAPE;
+  if (!(lambda > 0.f && lambda <= kMaxLambdaTc)) return DVLP_ERR_BAD_ARG;
+  if ((rc = device_ok())) return rc;
+  Workspace L = make_workspace(Bv, Bt, R, W, d, in_dtype, kPathTc3, false, n_per_group);
+  if (!workspace || workspace_bytes < L.total) return DVLP_ERR_WORKSPACE;
+  if ((uintptr_t)workspace & 255) return DVLP_ERR_MISALIGNED;
+  char* ws = (char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    ProfScope p(kProfPrep, st);
+    if ((rc = run_prep3(im, s, im_mask, s_mask, Bv, Bt, R, W, d, lambda, in_dtype, ws, L, st, n_per_group))) return rc;
+  }
+  ProfScope p(kProfFwd, st);
+  const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
+  const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
+  return run_pair_fwd3(vb, tb, Bv, Bt, R, W, d, lambda, focal_equal, scores, ws, L, false, st, n_per_group);
 }
 
 int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt,

@@ -125,7 +125,7 @@ enum Path { kPathGeneric = 0, kPathTc2 = 2, kPathTc3 = 3 };   // fp32 CUDA cores
 struct Shape3 { int NB, NQ, WP, TPT, Rp, nch; };
 bool shape3(int R, int W, int d, Shape3* s);
 
-Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int path, bool train = true);
+Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int path, bool train = true, int n_t = 0);
 
 // arguments of the generic pair kernels
 struct PairArgs {

@@ -74,6 +74,7 @@ constexpr uint32_t cS = 0, cY2 = 128, cC = 256;
 
 struct Args {
   int Bv, Bt, R, W, Rp, nch, tiles;
+  int grouped, n_t, tpg;           // grouped mode (multiple choice): video g against ITS n_t texts only; tpg tiles per group
   long long total_units;
   const float *alpha3, *m2v3;      // [Bv][Rp]   (0 / -1e30 beyond R)
   const float *beta3, *m2t3;       // [tiles][128] in tile-row order (0 / -1e30 for padded words and absent texts)
@@ -154,12 +155,17 @@ k_pair_fwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         int jt_prev = -1;
         for (int k = 0; k < n_units; ++k) {
           const long long u = u0 + k;
-          const int jt = (int)(u / a.Bv), i = (int)(u - (long long)jt * a.Bv);
+          // dense: unit = text tile * Bv + video (text-major);  grouped: unit = tile, its video = tile / tpg
+          const int jt = a.grouped ? (int)u : (int)(u / a.Bv);
+          const int i = a.grouped ? jt / a.tpg : (int)(u - (long long)jt * a.Bv);
           if (jt != jt_prev) {
             // new text tile: every consumer of the old one (S / Y2 products, beta / m2t readers) finished unit k-1
             if (k > 0) mbar_wait(bar(UNIT_DONE), (k - 1) & 1);
+            // first text of the tile (grouped: tile tt of group g starts at text g * n_t + tt * TPT; the rows past the
+            // group's last text belong to the next group: computed and never stored)
+            const int j0 = a.grouped ? (jt / a.tpg) * a.n_t + (jt % a.tpg) * TPT : jt * TPT;
             mbar_arrive_expect_tx(bar(TJ_FULL), 6 * kTileBytes + 1024);
-            for (int c = 0; c < 4; ++c) tma_load_3d(sbase + L::T + c * kTileBytes, &mapT, c * 64, 0, jt * TPT, bar(TJ_FULL));
+            for (int c = 0; c < 4; ++c) tma_load_3d(sbase + L::T + c * kTileBytes, &mapT, c * 64, 0, j0, bar(TJ_FULL));
             for (int c = 0; c < 2; ++c) tma_load_2d(sbase + L::GBD + c * kTileBytes, &mapGBD, c * 64, jt * kRows, bar(TJ_FULL));
             bulk_load(sbase + L::BETA, a.beta3 + (size_t)jt * kRows, 512, bar(TJ_FULL));
             bulk_load(sbase + L::M2T, a.m2t3 + (size_t)jt * kRows, 512, bar(TJ_FULL));
@@ -228,7 +234,7 @@ k_pair_fwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         __syncwarp();
       };
       for (int k = 0; k < n_units; ++k) {
-        const int jt = (int)((u0 + k) / a.Bv);
+        const int jt = a.grouped ? (int)(u0 + k) : (int)((u0 + k) / a.Bv);
         if (jt != jt_prev) { mbar_wait(bar(TJ_FULL), tj_loads & 1); ++tj_loads; jt_prev = jt; }
         for (int c = 0; c < nch; ++c) issue_S(nS++, true);
         for (int c = 0; c < nch; ++c) {
@@ -275,7 +281,8 @@ k_pair_fwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
 
     for (int k = 0; k < n_units; ++k) {
       const long long u = u0 + k;
-      const int jt = (int)(u / a.Bv), i = (int)(u - (long long)jt * a.Bv);
+      const int jt = a.grouped ? (int)u : (int)(u / a.Bv);
+      const int i = a.grouped ? jt / a.tpg : (int)(u - (long long)jt * a.Bv);
       if (jt != jt_prev) {
         mbar_wait(bar(TJ_FULL), tj_loads & 1); ++tj_loads; jt_prev = jt;
         beta_m = s_beta[m]; m2t_m = s_m2t[m];
@@ -478,14 +485,17 @@ k_pair_fwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       if (lane == 0) s_fin[cw] = acc_t2i;
       named_bar_sync(1, 128 * NG);
       if (cw == 0 && lane < TPT) {
-        const int j = jt * TPT + lane;
-        if (j < a.Bt) {
+        // dense: text j of the batch, scores (Bv, Bt);  grouped: option jj of group i, scores (groups, n_t)
+        const int jj = a.grouped ? (jt % a.tpg) * TPT + lane : jt * TPT + lane;
+        const bool ok = a.grouped ? jj < a.n_t : jj < a.Bt;
+        const int j = jj;
+        if (ok) {
           float i2t = 0.f, t2i = 0.f;
 #pragma unroll
           for (int qq = 0; qq < NQ; ++qq) i2t += s_fin[NW + lane * NQ + qq];
 #pragma unroll
           for (int gg = 0; gg < NG; ++gg) t2i += s_fin[gg * 4 + lane * NQ];
-          a.scores[(size_t)i * a.Bt + j] = i2t * a.inv_W + t2i * a.inv_R;     // means over the REAL counts (loss.py:318,327)
+          a.scores[(size_t)i * (a.grouped ? a.n_t : a.Bt) + j] = i2t * a.inv_W + t2i * a.inv_R;   // means over the REAL counts (loss.py:318,327)
         }
       }
       __syncwarp();
@@ -582,11 +592,14 @@ static int launch(const CUtensorMap& mV, const CUtensorMap& mT, const CUtensorMa
 }
 }  // namespace tf3
 
+// n_t == 0: dense (every video against every text).  n_t > 0: GROUPED -- video g against texts [g n_t, (g+1) n_t) only
+// (multiple-choice evaluation, trainer/trainer_dist.py:792-829); Bt = Bv * n_t, scores (Bv, n_t).
 int run_pair_fwd3(const void* vb, const void* tb, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
-                  float* scores, char* ws, const Workspace& Lw, bool save, cudaStream_t st) {
+                  float* scores, char* ws, const Workspace& Lw, bool save, cudaStream_t st, int n_t) {
   Shape3 s3;
   if (!shape3(R, W, d, &s3)) return DVLP_ERR_BAD_SHAPE;
-  const int tiles = (Bt + s3.TPT - 1) / s3.TPT;
+  const int tpg = n_t > 0 ? (n_t + s3.TPT - 1) / s3.TPT : 0;
+  const int tiles = n_t > 0 ? Bv * tpg : (Bt + s3.TPT - 1) / s3.TPT;
   CUtensorMap mV, mT, mG;
   int rc;
   if ((rc = make_map_items(&mV, vb, 256, (uint64_t)R, (uint64_t)Bv, (uint32_t)s3.NB, 1))) return rc;
@@ -594,7 +607,8 @@ int run_pair_fwd3(const void* vb, const void* tb, int Bv, int Bt, int R, int W, 
   if ((rc = make_map_2d(&mG, ws + Lw.gbd3, (uint64_t)tiles * 128, 128, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   tf3::Args a{};
   a.Bv = Bv; a.Bt = Bt; a.R = R; a.W = W; a.Rp = s3.Rp; a.nch = s3.nch; a.tiles = tiles;
-  a.total_units = (long long)tiles * Bv;
+  a.grouped = n_t > 0 ? 1 : 0; a.n_t = n_t; a.tpg = tpg;
+  a.total_units = n_t > 0 ? (long long)tiles : (long long)tiles * Bv;
   a.alpha3 = (const float*)(ws + Lw.alpha3); a.m2v3 = (const float*)(ws + Lw.m2v3);
   a.beta3 = (const float*)(ws + Lw.beta3); a.m2t3 = (const float*)(ws + Lw.m2t3);
   a.lam2 = lambda * kLog2e; a.inv_R = 1.f / (float)R; a.inv_W = 1.f / (float)W; a.focal = focal;

@@ -355,7 +355,7 @@ int run_prep(const void* im, const void* s, const float* im_mask, const float* s
 __global__ void __launch_bounds__(256) k_pack3(const float* __restrict__ alpha, const float* __restrict__ m2v,
                                                const float* __restrict__ beta, const float* __restrict__ m2t,
                                                const __nv_bfloat16* __restrict__ gtb, int Bv, int Bt, int R, int W, int Rp,
-                                               int WP, int TPT, int tiles, float* __restrict__ alpha3,
+                                               int WP, int TPT, int tiles, int n_t, int tpg, float* __restrict__ alpha3,
                                                float* __restrict__ m2v3, float* __restrict__ beta3,
                                                float* __restrict__ m2t3, __nv_bfloat16* __restrict__ gbd3) {
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,16 +367,17 @@ __global__ void __launch_bounds__(256) k_pack3(const float* __restrict__ alpha, 
   }
   for (size_t e = t0; e < (size_t)tiles * 128; e += stride) {
     const int row = (int)(e & 127), tile = (int)(e >> 7);
-    const int ts = row / WP, w = row - ts * WP, j = tile * TPT + ts;
-    const bool ok = j < Bt && w < W;
+    // texts of a tile: tile tt of group g holds texts g n_t + tt TPT + slot (dense: one group of Bt texts)
+    const int ts = row / WP, w = row - ts * WP, jg = (tile % tpg) * TPT + ts, j = (tile / tpg) * n_t + jg;
+    const bool ok = jg < n_t && j < Bt && w < W;
     beta3[e] = ok ? beta[(size_t)j * W + w] : 0.f;
     m2t3[e] = ok ? m2t[(size_t)j * W + w] : -1e30f;
   }
   for (size_t e = t0; e < (size_t)tiles * 128 * 64; e += stride) {       // two bf16 columns per thread
     const int col = (int)(e & 63) * 2, row = (int)((e >> 6) & 127), tile = (int)(e >> 13);
-    const int ts = row / WP, w = row - ts * WP, j = tile * TPT + ts;
+    const int ts = row / WP, w = row - ts * WP, jg = (tile % tpg) * TPT + ts, j = (tile / tpg) * n_t + jg;
     float v[2] = {0.f, 0.f};
-    if (j < Bt && w < W) {
+    if (jg < n_t && j < Bt && w < W) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = col + h, cs = c / WP, w2 = c - cs * WP;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(256) k_pack3(const float* __restrict__ alpha, 
 }
 
 int run_prep3(const void* im, const void* s, const float* im_mask, const float* s_mask, int Bv, int Bt, int R, int W,
-              int d, float lambda, int in_dtype, char* ws, const Workspace& L, cudaStream_t st) {
+              int d, float lambda, int in_dtype, char* ws, const Workspace& L, cudaStream_t st, int n_t) {
   Shape3 s3;
   if (!shape3(R, W, d, &s3)) return DVLP_ERR_BAD_SHAPE;
   const __nv_bfloat16* vb = (const __nv_bfloat16*)im;
@@ -422,12 +423,13 @@ int run_prep3(const void* im, const void* s, const float* im_mask, const float* 
     k_gram_tile<<<Bt, 256, smem, st>>>(tb, beta, W, d, nullptr, (__nv_bfloat16*)(ws + L.gtb));
     DVLP_LAUNCH_OK();
   }
-  const int tiles = (Bt + s3.TPT - 1) / s3.TPT;
+  const int tpg = n_t > 0 ? (n_t + s3.TPT - 1) / s3.TPT : (Bt + s3.TPT - 1) / s3.TPT;
+  const int tiles = n_t > 0 ? Bv * tpg : tpg;
   const size_t work = (size_t)tiles * 128 * 64;
   int grid = (int)((work + 256 * 4 - 1) / (256 * 4));
   grid = grid < 1 ? 1 : (grid > 148 * 8 ? 148 * 8 : grid);
   k_pack3<<<grid, 256, 0, st>>>(alpha, (const float*)(ws + L.m2v), beta, (const float*)(ws + L.m2t),
-                                (const __nv_bfloat16*)(ws + L.gtb), Bv, Bt, R, W, s3.Rp, s3.WP, s3.TPT, tiles,
+                                (const __nv_bfloat16*)(ws + L.gtb), Bv, Bt, R, W, s3.Rp, s3.WP, s3.TPT, tiles, n_t > 0 ? n_t : Bt, tpg,
                                 (float*)(ws + L.alpha3), (float*)(ws + L.m2v3), (float*)(ws + L.beta3),
                                 (float*)(ws + L.m2t3), (__nv_bfloat16*)(ws + L.gbd3));
   DVLP_LAUNCH_OK();

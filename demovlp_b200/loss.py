@@ -42,6 +42,15 @@ class RWALoss(nn.Module):
         return ops.rw_scores(im, s, im_m, s_m, lam=self.lambda_softmax,
                              focal_equal=(self.focal_type == "equal"), impl=self.impl)
 
+    def get_sim_grouped(self, im, s, im_m, s_m, n_options):
+        """Batched multiple-choice scoring (trainer/trainer_dist.py:792-829): ``im`` (Q, R, d) holds the video of each of
+        Q questions ONCE (the reference expands it n_options times), ``s`` (Q * n_options, W, d) the options, question-
+        major.  Returns (Q, n_options) = row 0 of the reference's per-question ``local_sims_batch``; the predicted answer
+        is ``(global_row + local).argmax(1)`` exactly as ``sims_batch[0].max(0)[1]`` there.  Forward only."""
+        with torch.no_grad():
+            return ops.rw_scores_grouped(im, s, im_m, s_m, n_options, lam=self.lambda_softmax,
+                                         focal_equal=(self.focal_type == "equal"))
+
     def get_sim_by_segment(self, img_feats, lang_feats, img_mask, lang_length, cap_mask,
                            segment=8, device="cpu", rows_per_launch=256):
         """float64 numpy (n_image, n_caption) eval matrix (:73-103).

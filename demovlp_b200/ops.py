@@ -107,6 +107,41 @@ def rw_scores(im, s, im_mask, s_mask=None, lam=20.0, focal_equal=True, impl="aut
     return _RWScores.apply(im, s, _prep_mask(im_mask, None), _prep_mask(s_mask, None), lam, focal_equal, impl)
 
 
+def rw_scores_grouped(im, s, im_mask, s_mask, n_per_group, lam=20.0, focal_equal=True):
+    """Forward-only scores of G groups in one launch: video g against ITS n_per_group texts (group-major ``s``).
+
+    (G, n_per_group) fp32.  This is the multiple-choice evaluation of trainer/trainer_dist.py:792-829 batched over the
+    questions (the reference expands one video n_options times and scores a 5 x 5 problem per question).  Shapes outside
+    the large-shape tcgen05 kernel are served group by group through the dense forward-only entry point."""
+    im, s = _prep_embed(im), _prep_embed(s)
+    if s_mask is None:
+        s_mask = torch.ones(s.shape[0], s.shape[1], device=s.device)
+    im_mask, s_mask = _prep_mask(im_mask, None), _prep_mask(s_mask, None)
+    _lib.require_cuda(im, s, im_mask, s_mask)
+    lib = _lib.load()
+    G, R, d = im.shape
+    Bt, W, d2 = s.shape
+    if d2 != d or Bt != G * n_per_group or im_mask.shape != (G, R) or s_mask.shape != (Bt, W):
+        raise RuntimeError(f"shape mismatch: im {tuple(im.shape)} s {tuple(s.shape)} n_per_group {n_per_group}")
+    if im.dtype != s.dtype:
+        im, s = im.float(), s.float()
+    dt = _lib.dtype_code(im)
+    nbytes = lib.dvlp_rw_grouped_workspace_bytes(G, n_per_group, R, W, d, dt)
+    if nbytes == 0:         # generic kernels, one (1 x n_per_group) problem per group
+        rows = [rw_scores_fwd_raw(im[g:g + 1], s[g * n_per_group:(g + 1) * n_per_group], im_mask[g:g + 1],
+                                  s_mask[g * n_per_group:(g + 1) * n_per_group], lam, focal_equal, "auto", train=False)[0]
+                for g in range(G)]
+        return torch.cat(rows, 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=im.device)
+    scores = torch.empty(G, n_per_group, dtype=torch.float32, device=im.device)
+    with torch.cuda.device(im.device):
+        rc = lib.dvlp_rw_scores_grouped_infer(_lib.ptr(im), _lib.ptr(s), _lib.ptr(im_mask), _lib.ptr(s_mask), G, n_per_group,
+                                              R, W, d, float(lam), int(focal_equal), dt, _lib.ptr(scores), _lib.ptr(ws),
+                                              nbytes, _lib.stream_ptr())
+    _lib.check(rc, "rw_scores_grouped_infer")
+    return scores
+
+
 def rwa_tail_raw(scores, lam, row_offset, n_total, want_grad=True):
     """(sum_i KL_i / n_total, d_scores or None) for a block of score rows."""
     _lib.require_cuda(scores)

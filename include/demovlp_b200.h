@@ -110,6 +110,20 @@ int dvlp_rw_scores_infer(const void* im, const void* s, const float* im_mask, co
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Grouped forward (multiple-choice evaluation, trainer/trainer_dist.py:792-829): the reference expands ONE video
+ * n_options times and calls get_sim on a 5 x 5 problem per question; here n_groups questions go through ONE launch:
+ *   im (n_groups, R, d): the video of every question      s (n_groups * n_per_group, W, d): its options, group-major
+ *   scores (n_groups, n_per_group) fp32: scores[g][o] = score(video g, option o of question g)
+ * -- exactly row 0 of the reference's per-question local_sims_batch.  tcgen05 large-shape kernel only (d = 256,
+ * W <= 128; dvlp_rw_grouped_workspace_bytes returns 0 for other shapes, which callers serve question by question
+ * with dvlp_rw_scores_infer).
+ */
+size_t dvlp_rw_grouped_workspace_bytes(int n_groups, int n_per_group, int R, int W, int d, int in_dtype);
+int dvlp_rw_scores_grouped_infer(const void* im, const void* s, const float* im_mask, const float* s_mask,
+                                 int n_groups, int n_per_group, int R, int W, int d, float lambda, int focal_equal,
+                                 int in_dtype, float* scores, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Backward of dvlp_rw_scores_fwd (what autograd does through model/loss.py:209-330):
  * given d_scores (Bv, Bt) fp32 produces d_im (Bv, R, d) and d_s (Bt, W, d) in `out_dtype`
  * (both overwritten; DVLP_F32 always, DVLP_BF16 on the tcgen05 path, else DVLP_ERR_BAD_DTYPE).

@@ -426,6 +426,11 @@ def test_validation_feed_matches_segmented_eval():
     assert got.dtype == np.float64 and got.shape == (40, 40)
     assert np.array_equal(got, want)
     assert M.t2v_metrics(got) == M.t2v_metrics(want)
+    # ... and equals what the ORACLE computes for the matrix the trainer builds (trainer_dist.py:369-385: text x video
+    # cosine matrix + video x text local scores, orientation quirk kept), within the score tolerance
+    with torch.no_grad():
+        oracle = (O.sim_matrix(b.g_text, b.g_vid).double() + O.pair_scores(b.im, b.s, b.im_mask, b.s_mask, focal="equal").double()).numpy()
+    assert np.abs(got - oracle).max() < SCORE_TOL
 
 
 LARGE_SHAPES = [(288, 64), (240, 99), (30, 99)]     # config 5 and the reference's shipped fine-tune / pre-train shapes
@@ -560,3 +565,34 @@ def test_eval_1000_end_to_end_vs_reference_matrix(shape):
                                        R1=got["R1"], R1_ref=ref["R1"], MeanR=got["MeanR"], MeanR_ref=ref["MeanR"]))
     assert mism <= 80                              # 8 %: score noise 1e-4 against row gaps of ~5e-4
     assert abs(got["MeanR"] - ref["MeanR"]) < 0.5 and abs(got["R1"] - ref["R1"]) <= 0.5
+
+
+@pytest.mark.parametrize("name", ["mc_q64_r80_w32", "mc_q16_r240_w99", "mc_q24_r30_w99"])
+def test_multiple_choice_batched_vs_reference_fixture(name):
+    """the multiple-choice evaluation (trainer/trainer_dist.py:792-829: one video expanded 5 x, get_sim per
+    question) as ONE grouped launch of the large-shape tcgen05 forward for all questions, against fixtures minted by
+    replaying the reference question by question (oracle/make_golden_mc.py): score rows 2e-3, predictions equal."""
+    g = load_golden(name)
+    Q, R, W, d, seed = (int(x) for x in g["meta"][:5])
+    n_opt = int(g["meta"][6])
+    b = synth.make_batch(Q * n_opt, R, W, d, seed, float(g["meta"][5]))
+    assert abs(float(b.im.double().sum()) - g["checksum"][0]) < 1e-6
+    perm = torch.from_numpy(g["perm"]).reshape(-1)
+    vid = torch.arange(Q) * n_opt
+    dvc = "cuda"
+    mod = L.RWALoss(focal_type="equal")
+    im = b.im[vid].to(torch.bfloat16).to(dvc)
+    s = b.s[perm].to(torch.bfloat16).to(dvc)
+    local = mod.get_sim_grouped(im, s, b.im_mask[vid].to(dvc), b.s_mask[perm].to(dvc), n_opt)
+    assert local.shape == (Q, n_opt)
+    err = float(np.abs(local.cpu().numpy() - g["local_row0"]).max())
+    assert err < SCORE_TOL
+    # the per-question route (what the reference trainer calls) gives the same numbers
+    q = 3
+    one = mod.get_sim(im[q:q + 1].expand(n_opt, -1, -1).contiguous(), s[q * n_opt:(q + 1) * n_opt],
+                      b.im_mask[vid][q:q + 1].expand(n_opt, -1).contiguous().to(dvc), None, b.s_mask[perm][q * n_opt:(q + 1) * n_opt].to(dvc))
+    assert (one[0] - local[q]).abs().max() < 2e-4
+    pred = (torch.from_numpy(g["global_row0"]).to(dvc) + local).argmax(1).cpu().numpy()
+    _record("multiple_choice", dict(case=name, questions=Q, max_abs_score_err=err,
+                                    pred_mismatches=int((pred != g["pred"]).sum())))
+    np.testing.assert_array_equal(pred, g["pred"])
