@@ -1,5 +1,6 @@
 // extern "C" entry points declared in include/demovlp_b200.h: validation + dispatch.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -62,14 +63,48 @@ int run_p2p_check(const void*, cudaStream_t);
 // tcgen05 path: pair_fwd2.cu, pair_bwd2.cu, grad_gemm2.cu
 int run_pair_fwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
                   float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
-int run_pair_bwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda,
+int run_pair_bwd2(const void* im_bf16, const void* s_bf16, int v0, int nv, int Bt, int R, int W, int d, float lambda,
                   const float* d_scores, char* ws, const Workspace& L, cudaStream_t st);
-int run_grad_gemm2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, char* ws,
+int run_grad_gemm2(const void* im_bf16, const void* s_bf16, int v0, int nv, int Bt, int R, int W, int d, char* ws,
                    const Workspace& L, cudaStream_t st);
 void* g_trace_buffer = nullptr;   // set through dvlp_debug_set_trace (tools/trace_tiles.py)
 
 // shapes served by the tcgen05 kernels: d = 256, W = 32 words, R a multiple of 16 in [32, 80]
 bool tc_supported(int R, int W, int d) { return d == 256 && W == 32 && (R == 80 || R == 64 || R == 48 || R == 32); }
+
+// The small-shape backward hands its bf16 gradient tiles P (20 KB per (video, 4-text tile) at R = 80) to the gradient
+// GEMMs through memory: 84 MB at config 2, 671 MB per rank at config 3 -- more than the 126 MB L2 keeps.  The backward
+// can therefore walk the videos in CHUNKS whose P tiles stay in L2 (pair kernel of a chunk, then both GEMMs of that
+// chunk, all re-using ONE chunk-sized buffer): DVLP_P_CHUNK_MB = target chunk size in MB.  MEASURED on B200 (round 2,
+// config 3 on one GPU, 40 MB chunks = 8 videos): the pair kernel gets 18 % slower (148 persistent CTAs x ~14 units per
+// launch: pipeline fill / drain per launch) and the GEMMs 2.6 x slower (K loops of 7 tiles, split-K red.global adds),
+// 25.0 ms per step instead of 20.2 -- the re-reads cost less than the short launches, the GEMMs run at ~900 algorithmic
+// TFLOP/s unchunked and are not HBM-bound.  So chunking is OFF by default (0); the path stays for experiments.
+// Returns the videos per chunk (the same for workspace sizing and launch).
+int tc2_chunk_videos(int Bv, int Bt, int R) {
+  static const double target_mb = [] {
+    const char* e = getenv("DVLP_P_CHUNK_MB");
+    return e ? atof(e) : 0.0;
+  }();
+  if (!(target_mb > 0.0)) return Bv;
+  const int tiles = (Bt + 3) / 4;
+  const double per_video = (double)tiles * 128 * R * 2;
+  const double nvd = target_mb * 1048576.0 / per_video;
+  if (nvd >= (double)Bv) return Bv;
+  int nv = (int)nvd;
+  if (nv < 1) nv = 1;
+  const int n_chunks = (Bv + nv - 1) / nv;
+  nv = (Bv + n_chunks - 1) / n_chunks;               // even chunks
+  // prefer a size whose unit count fills the 148 persistent CTAs evenly
+  int best = nv;
+  double best_eff = 0.0;
+  for (int c = nv; c >= 1 && c >= nv - nv / 4; --c) {
+    const long long units = (long long)c * tiles;
+    const double eff = (double)units / (double)(((units + 147) / 148) * 148);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
+  }
+  return best;
+}
 
 Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int path, bool train, int n_t) {
   Workspace L{};
@@ -112,7 +147,8 @@ Workspace make_workspace(int Bv, int Bt, int R, int W, int d, int in_dtype, int 
     L.colv = take(units * s3.TPT * s3.Rp * 16);
   } else {
     const size_t units = (size_t)Bv * ((Bt + 3) / 4);
-    L.pa = take(tc2 && train ? units * R * 128 * 2 : 0);
+    const size_t p_units = tc2 && train ? (size_t)tc2_chunk_videos(Bv, Bt, R) * ((Bt + 3) / 4) : 0;    // one chunk of videos
+    L.pa = take(p_units * R * 128 * 2);
     L.rowv = take(tc2 && train ? units * 128 * 16 : 0);
     L.colv = take(tc2 && train ? units * 4 * R * 16 : 0);
     L.gbd = take(tc2 ? (size_t)((Bt + 3) / 4) * 128 * 128 * 2 : 0);
@@ -387,13 +423,18 @@ int dvlp_rw_scores_bwd(const void* im, const void* s, const float* im_mask, cons
   if (path == kPathTc2) {
     const void* vb = in_dtype == DVLP_BF16 ? im : (const void*)(ws + L.vb);
     const void* tb = in_dtype == DVLP_BF16 ? s : (const void*)(ws + L.tb);
-    {
-      ProfScope pb(kProfBwd, st);
-      if ((rc = run_pair_bwd2(vb, tb, Bv, Bt, R, W, d, lambda, d_scores, ws, L, st))) return rc;
-    }
-    {
-      ProfScope pg(kProfGG, st);
-      if ((rc = run_grad_gemm2(vb, tb, Bv, Bt, R, W, d, ws, L, st))) return rc;
+    // chunks of videos whose P tiles stay in L2 between the pair kernel and the gradient GEMMs (tc2_chunk_videos)
+    const int chunk = tc2_chunk_videos(Bv, Bt, R);
+    for (int v0 = 0; v0 < Bv; v0 += chunk) {
+      const int nv = Bv - v0 < chunk ? Bv - v0 : chunk;
+      {
+        ProfScope pb(kProfBwd, st);
+        if ((rc = run_pair_bwd2(vb, tb, v0, nv, Bt, R, W, d, lambda, d_scores, ws, L, st))) return rc;
+      }
+      {
+        ProfScope pg(kProfGG, st);
+        if ((rc = run_grad_gemm2(vb, tb, v0, nv, Bt, R, W, d, ws, L, st))) return rc;
+      }
     }
     dgt_swz = 1;
     prescaled = 1;

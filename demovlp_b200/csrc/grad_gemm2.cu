@@ -250,9 +250,12 @@ static int launch_mode(const CUtensorMap& mP, const CUtensorMap& mX, Args a, int
   return DVLP_OK;
 }
 
+// videos [v0, v0 + Bv): their P tiles sit at the start of the (chunk-sized) P buffer; dV' rows of the range are written,
+// dT' accumulates over the range
 template <int R>
-static int launch(const void* vb, const void* tb, int Bv, int Bt, int W, char* ws, const Workspace& Lw, cudaStream_t st) {
+static int launch(const void* vb_all, const void* tb, int v0, int Bv, int Bt, int W, char* ws, const Workspace& Lw, cudaStream_t st) {
   const int tiles = (Bt + 3) / 4;
+  const void* vb = (const char*)vb_all + (size_t)v0 * R * kD * 2;
   const long long units = (long long)Bv * tiles;
   CUtensorMap mP, mT, mV;
   int rc;
@@ -269,10 +272,11 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, int W, char* w
   static const int forced = [] { const char* e = getenv("DVLP_GG_PAIR"); return e ? atoi(e) : -1; }();
   const bool pair = forced >= 0 ? forced != 0 : tiles >= 128;     // measured: -13 % at 256 tiles, break-even at 64
   // dV' (Bv, R, d): overwritten unless split;  dT' (Bt*W, d): accumulated (the caller zeroes it)
-  a.out = (float*)(ws + Lw.dvh); a.accumulate = 0;
+  a.out = (float*)(ws + Lw.dvh) + (size_t)v0 * R * kD; a.accumulate = 0;
   const size_t dv_bytes = (size_t)Bv * R * kD * 4;
+  // (a chunk of few videos: split the K loop over CTAs so that the launch still fills the GPU)
   rc = pair ? launch_mode<R, MODE_V, 2>(mP, mT, a, Bv, tiles, sms, true, dv_bytes, st)
-            : launch_mode<R, MODE_V, 1>(mP, mT, a, Bv, tiles, sms, false, dv_bytes, st);
+            : launch_mode<R, MODE_V, 1>(mP, mT, a, Bv, tiles, sms, 2 * Bv <= sms, dv_bytes, st);
   if (rc) return rc;
   a.out = (float*)(ws + Lw.dth); a.accumulate = 1;
   rc = pair ? launch_mode<R, MODE_T, 2>(mP, mV, a, tiles, Bv, sms, true, 0, st)
@@ -282,14 +286,14 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, int W, char* w
 }  // namespace gg2
 
 // dV' (overwritten) and dT' (accumulated: the caller zeroes it) from the P tiles pair_bwd2.cu stored
-int run_grad_gemm2(const void* vb, const void* tb, int Bv, int Bt, int R, int W, int d, char* ws, const Workspace& L,
+int run_grad_gemm2(const void* vb, const void* tb, int v0, int nv, int Bt, int R, int W, int d, char* ws, const Workspace& L,
                   cudaStream_t st) {
   if (d != gg2::kD || W != 32) return DVLP_ERR_BAD_SHAPE;
   switch (R) {
-    case 80: return gg2::launch<80>(vb, tb, Bv, Bt, W, ws, L, st);
-    case 64: return gg2::launch<64>(vb, tb, Bv, Bt, W, ws, L, st);
-    case 48: return gg2::launch<48>(vb, tb, Bv, Bt, W, ws, L, st);
-    case 32: return gg2::launch<32>(vb, tb, Bv, Bt, W, ws, L, st);
+    case 80: return gg2::launch<80>(vb, tb, v0, nv, Bt, W, ws, L, st);
+    case 64: return gg2::launch<64>(vb, tb, v0, nv, Bt, W, ws, L, st);
+    case 48: return gg2::launch<48>(vb, tb, v0, nv, Bt, W, ws, L, st);
+    case 32: return gg2::launch<32>(vb, tb, v0, nv, Bt, W, ws, L, st);
   }
   return DVLP_ERR_BAD_SHAPE;
 }

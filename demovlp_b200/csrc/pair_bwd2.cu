@@ -581,29 +581,34 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return DVLP_OK;
 }
 
+// videos [v0, v0 + Bv) of the batch: every per-video array is offset, the P tiles of the range go to the start of the
+// (chunk-sized) P buffer
 template <int R>
-static int launch(const void* vb, const void* tb, int Bv, int Bt, float lambda, const float* d_scores, char* ws,
+static int launch(const void* vb_all, const void* tb, int v0, int Bv, int Bt, float lambda, const float* d_scores_all, char* ws,
                   const Workspace& Lw, cudaStream_t st) {
   using L = Lay<R>;
   CUtensorMap mV, mT, mGV, mGBD, mP;
   int rc;
   Args a{};
   a.Bv = Bv; a.Bt = Bt;
+  const void* vb = (const char*)vb_all + (size_t)v0 * R * kD * 2;
+  const float* d_scores = d_scores_all + (size_t)v0 * Bt;
   a.tiles_per_video = (Bt + kTPT - 1) / kTPT;
   a.total_units = (long long)Bv * a.tiles_per_video;
   if ((rc = make_map(&mV, vb, (uint64_t)Bv * R, kD, R, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&mT, tb, (uint64_t)Bt * kW, kD, kRows, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map(&mGV, ws + Lw.gvb, (uint64_t)Bv * R, R, R, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&mGV, ws + Lw.gvb + (size_t)v0 * R * R * 2, (uint64_t)Bv * R, R, R, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&mGBD, ws + Lw.gbd, (uint64_t)a.tiles_per_video * kRows, kRows, kRows, 64, CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
   // P spill: [unit][128 words][R regions] bf16, one 16-column box per chunk
   if ((rc = make_map(&mP, ws + Lw.pa, (uint64_t)a.total_units * kRows, R, kRows, 16, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  a.alpha = (const float*)(ws + Lw.alpha); a.beta = (const float*)(ws + Lw.beta);
-  a.m2v = (const float*)(ws + Lw.m2v); a.m2t = (const float*)(ws + Lw.m2t);
+  a.alpha = (const float*)(ws + Lw.alpha) + (size_t)v0 * R; a.beta = (const float*)(ws + Lw.beta);
+  a.m2v = (const float*)(ws + Lw.m2v) + (size_t)v0 * R; a.m2t = (const float*)(ws + Lw.m2t);
   a.d_scores = d_scores;
-  a.rowv = (const float4*)(ws + Lw.rowv); a.colv = (const float4*)(ws + Lw.colv);
+  a.rowv = (const float4*)(ws + Lw.rowv) + (size_t)v0 * a.tiles_per_video * kRows;
+  a.colv = (const float4*)(ws + Lw.colv) + (size_t)v0 * a.tiles_per_video * kTPT * R;
   a.lam = lambda; a.lam2 = lambda * kLog2e;
-  a.dgv = (float*)(ws + Lw.dgv); a.dgt = (float*)(ws + Lw.dgt);
+  a.dgv = (float*)(ws + Lw.dgv) + (size_t)v0 * R * R; a.dgt = (float*)(ws + Lw.dgt);
   a.trace = (long long*)g_trace_buffer;
   int dev = 0, sms = 148;
   DVLP_CUDA_OK(cudaGetDevice(&dev));
@@ -624,14 +629,15 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, float lambda, 
 }
 }  // namespace tb2
 
-int run_pair_bwd2(const void* vb, const void* tb, int Bv, int Bt, int R, int W, int d, float lambda,
+// backward of the videos [v0, v0 + nv) against all Bt texts (vb, d_scores: the whole batch)
+int run_pair_bwd2(const void* vb, const void* tb, int v0, int nv, int Bt, int R, int W, int d, float lambda,
                   const float* d_scores, char* ws, const Workspace& L, cudaStream_t st) {
   if (d != tb2::kD || W != tb2::kW) return DVLP_ERR_BAD_SHAPE;
   switch (R) {
-    case 80: return tb2::launch<80>(vb, tb, Bv, Bt, lambda, d_scores, ws, L, st);
-    case 64: return tb2::launch<64>(vb, tb, Bv, Bt, lambda, d_scores, ws, L, st);
-    case 48: return tb2::launch<48>(vb, tb, Bv, Bt, lambda, d_scores, ws, L, st);
-    case 32: return tb2::launch<32>(vb, tb, Bv, Bt, lambda, d_scores, ws, L, st);
+    case 80: return tb2::launch<80>(vb, tb, v0, nv, Bt, lambda, d_scores, ws, L, st);
+    case 64: return tb2::launch<64>(vb, tb, v0, nv, Bt, lambda, d_scores, ws, L, st);
+    case 48: return tb2::launch<48>(vb, tb, v0, nv, Bt, lambda, d_scores, ws, L, st);
+    case 32: return tb2::launch<32>(vb, tb, v0, nv, Bt, lambda, d_scores, ws, L, st);
   }
   return DVLP_ERR_BAD_SHAPE;
 }
