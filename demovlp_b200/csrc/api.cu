@@ -60,6 +60,9 @@ int run_p2p_allgather(void* const*, int, int, int, const void* const*, const siz
 int run_p2p_sum_scalar(void* const*, int, int, const float*, float*, cudaStream_t);
 int run_p2p_reduce_scatter(void* const*, int, int, size_t, size_t, void*, int, cudaStream_t);
 int run_p2p_check(const void*, cudaStream_t);
+size_t proj_workspace_bytes(int M, int K, int in_dtype, int relu_in);
+int run_proj_fwd(const void* x, int in_dtype, int M, int K, const void* w_bf16, const float* bias, int relu_in, void* out,
+                 char* ws, cudaStream_t st);
 // tcgen05 path: pair_fwd2.cu, pair_bwd2.cu, grad_gemm2.cu
 int run_pair_fwd2(const void* im_bf16, const void* s_bf16, int Bv, int Bt, int R, int W, int d, float lambda, int focal,
                   float* scores, char* ws, const Workspace& L, bool save, cudaStream_t st);
@@ -531,6 +534,24 @@ int dvlp_rw_bwd_out_dtype_supported(int impl, int R, int W, int d, float lambda,
   int path = kPathGeneric;
   if (pick_path(impl, R, W, d, true, &path, lambda) != DVLP_OK || path != kPathTc2) return 0;
   return (d == 256 && (R % 16) == 0 && (W % 16) == 0 && R <= 128 && W <= 128) ? 1 : 0;   // run_grad_finalize_tc
+}
+
+size_t dvlp_proj_workspace_bytes(int M, int K, int in_dtype, int relu_in) {
+  if (M <= 0 || K <= 0 || (K % 64) != 0) return 0;
+  return proj_workspace_bytes(M, K, in_dtype, relu_in);
+}
+
+int dvlp_proj_fwd(const void* x, int in_dtype, int M, int K, int N, const void* w_bf16, const float* bias, int relu_in,
+                  void* out_bf16, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !w_bf16 || !out_bf16) return DVLP_ERR_NULL_POINTER;
+  if (M <= 0 || K <= 0 || (K % 64) != 0 || N != 256) return DVLP_ERR_BAD_SHAPE;
+  if (in_dtype != DVLP_F32 && in_dtype != DVLP_BF16) return DVLP_ERR_BAD_DTYPE;
+  if (((uintptr_t)x | (uintptr_t)w_bf16 | (uintptr_t)out_bf16) & 15) return DVLP_ERR_MISALIGNED;
+  if (!workspace || workspace_bytes < proj_workspace_bytes(M, K, in_dtype, relu_in)) return DVLP_ERR_WORKSPACE;
+  if ((uintptr_t)workspace & 255) return DVLP_ERR_MISALIGNED;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_proj_fwd(x, in_dtype, M, K, w_bf16, bias, relu_in, out_bf16, (char*)workspace, (cudaStream_t)stream);
 }
 
 size_t dvlp_p2p_control_bytes(void) { return 4096; }

@@ -167,6 +167,19 @@ int dvlp_normsoftmax_fwd_bwd(const float* x, int N, int M, float temperature,
                              float* loss, float* d_x, float* scratch, void* stream);
 
 /*
+ * Projection heads feeding the path: Y = act(X) W^T + b as one tcgen05 GEMM writing the bf16 rows the
+ * scoring kernels read.  Replaces txt_proj = Sequential(ReLU(), Linear(768, 256)) (model/model.py:40-43, applied at :88;
+ * relu_in = 1, bias given) and ObjectTransformer.proj = Linear(768, 256, bias=False) (model/object_transformer.py:381,
+ * :451; relu_in = 0, bias NULL).
+ *   x (M, K) fp32 or bf16 token rows (K a multiple of 64), w_bf16 (N = 256, K) bf16 row-major (nn.Linear.weight),
+ *   bias (256) fp32 or NULL, out_bf16 (M, 256) bf16, overwritten.  Forward only: the host mirror's backward
+ *   (demovlp_b200/proj.py) uses library GEMMs.
+ */
+size_t dvlp_proj_workspace_bytes(int M, int K, int in_dtype, int relu_in);
+int dvlp_proj_fwd(const void* x, int in_dtype, int M, int K, int N, const void* w_bf16, const float* bias, int relu_in,
+                  void* out_bf16, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Retrieval ranks (model/metric.py).  sims is the (Nq, Nv) float64 matrix the
  * trainer builds (trainer/trainer_dist.py:369-385), rows = text queries.
  *   t2v (metric.py:22-66):  ranks[i] = #{ j : sims[i][j] > sims[i][gt(i)] },  gt(i) = i / (Nq / Nv)

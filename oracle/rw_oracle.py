@@ -240,3 +240,14 @@ def sharded_reference(batch_fn, world, **loss_kw):
                   g_text=g_text.grad[r * b:(r + 1) * b], g_vid=g_vid.grad[r * b:(r + 1) * b])
              for r in range(world)]
     return (loss.detach(), g.detach(), l.detach()), grads
+
+
+def projection(tokens, weight, bias=None, relu_in=False):
+    """The projection heads in front of the path (test infrastructure): ``txt_proj = Sequential(ReLU(), Linear)``
+    (model/model.py:40-43, :88) with relu_in=True, ``ObjectTransformer.proj = Linear(bias=False)``
+    (model/object_transformer.py:381, :451) with relu_in=False; returns (global = token 0, local = tokens 1..) as
+    model/model.py:88-96 splits them."""
+    import torch.nn.functional as F
+    x = F.relu(tokens) if relu_in else tokens
+    y = F.linear(x, weight, bias)
+    return y[:, 0, ...], y[:, 1:, ...]

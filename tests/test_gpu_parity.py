@@ -596,3 +596,43 @@ def test_multiple_choice_batched_vs_reference_fixture(name):
     _record("multiple_choice", dict(case=name, questions=Q, max_abs_score_err=err,
                                     pred_mismatches=int((pred != g["pred"]).sum())))
     np.testing.assert_array_equal(pred, g["pred"])
+
+
+@pytest.mark.parametrize("case", [("text", 12, 99, True, True, torch.float32), ("video", 9, 240, False, False, torch.float32),
+                                  ("text_bf16", 5, 32, True, True, torch.bfloat16)])
+def test_fused_projection_heads_vs_oracle(case):
+    """txt_proj (ReLU + Linear(768, 256), model/model.py:40-43,88) and ObjectTransformer.proj (Linear(768, 256,
+    bias=False), model/object_transformer.py:381,451) as one tcgen05 GEMM with bf16 output, forward and backward, against
+    the oracle on the same bf16-rounded operands."""
+    from demovlp_b200.proj import FusedProjection
+    name, B, L, relu, bias, dtype = case
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(B, L + 1, 768, generator=gen)
+    mod = FusedProjection(768, 256, relu_in=relu, bias=bias)
+    with torch.no_grad():
+        mod.weight.copy_(mod.weight.to(torch.bfloat16).float())           # bf16-representable operands: exact products
+        x = x.to(torch.bfloat16).float()
+    xc = x.clone().requires_grad_(True)
+    wc = mod.weight.detach().clone().requires_grad_(True)
+    bc = mod.bias.detach().clone().requires_grad_(True) if bias else None
+    want_g, want_l = O.projection(xc, wc, bc, relu_in=relu)
+    wsum = torch.randn(B, L + 1, 256, generator=gen)
+    ((want_g * wsum[:, 0]).sum() + (want_l * wsum[:, 1:]).sum()).backward()
+    mod = mod.cuda()
+    xg = x.to(dtype).cuda().requires_grad_(True)
+    got_g, got_l = mod(xg)
+    assert got_g.dtype == torch.bfloat16 and got_l.shape == (B, L, 256)
+    ((got_g.float() * wsum[:, 0].cuda()).sum() + (got_l.float() * wsum[:, 1:].cuda()).sum()).backward()
+    assert rel_err(got_l.float().cpu(), want_l.detach()) < 4e-3            # one bf16 rounding of the output
+    assert rel_err(got_g.float().cpu(), want_g.detach()) < 4e-3
+    # (the output is bf16, so autograd hands the backward a bf16-rounded upstream gradient: 2^-9 relative)
+    assert rel_err(xg.grad.float().cpu(), xc.grad) < (1e-2 if dtype == torch.bfloat16 else 5e-3)
+    assert rel_err(mod.weight.grad.cpu(), wc.grad) < 5e-3
+    if bias:
+        assert rel_err(mod.bias.grad.cpu(), bc.grad) < 5e-3
+    # the projected rows feed the scoring kernels directly
+    if name == "text":
+        im = torch.randn(B, 30, 256, generator=gen).to(torch.bfloat16).cuda()
+        sc = ops.rw_scores(im, got_l.detach().contiguous(), torch.zeros(B, 30, device="cuda"), torch.zeros(B, L, device="cuda"))
+        ref = O.pair_scores(im.float().cpu(), got_l.detach().float().cpu(), torch.zeros(B, 30), torch.zeros(B, L))
+        assert (sc.cpu() - ref).abs().max() < SCORE_TOL
