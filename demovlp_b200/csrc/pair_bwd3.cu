@@ -157,6 +157,9 @@ k_pair_bwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
   const uint32_t tmem = *s_tmem;
 
   if (warp < 4) {
+    // register budget: the four control warps keep 40 registers each, the compute warps take what that frees
+    // (NB = 48: 384 threads x 152; NB = 32: 256 threads x 232 > the 255 cap, left alone)
+    if (NG == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
       // =============================== TMA producer ===============================
       if (elect_one()) {
@@ -271,6 +274,7 @@ k_pair_bwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     }
   } else {
     // ============================ compute warps ============================
+    if (NG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int cw = warp - 4;
     const int g = cw >> 2, q = cw & 3;
     const int m = q * 32 + lane;
