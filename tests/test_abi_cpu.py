@@ -103,3 +103,55 @@ def test_host_mirror_keeps_reference_signatures():
             ref_params = list(inspect.signature(getattr(L, cls).__init__).parameters)
             mine = list(inspect.signature(getattr(loss, cls).__init__).parameters)
             assert mine[:len(ref_params)] == ref_params, cls
+
+
+def test_kernel_path_selection_and_new_entry_points_without_gpu():
+    """Which pair kernels serve a shape is host logic (no device needed): small-shape tcgen05 kernels for W = 32 /
+    R in {32,48,64,80}, the large-shape streaming kernels for every other d = 256 shape they can tile (BASELINE config 5,
+    the reference's shipped R = 30 / 240 x W = 99), fp32 CUDA cores otherwise; plus argument validation of the grouped
+    (multiple-choice), projection and peer-check entry points."""
+    lib = _lib.load()
+    for R in (32, 48, 64, 80):
+        assert lib.dvlp_rw_path(R, 32, 256, 1) == 2 and lib.dvlp_rw_path(R, 32, 256, 0) == 2
+    for R, W in ((288, 64), (240, 99), (30, 99), (17, 9), (100, 20), (130, 128), (96, 32)):
+        assert lib.dvlp_rw_path(R, W, 256, 1) == 3 and lib.dvlp_rw_path(R, W, 256, 0) == 3, (R, W)
+        assert lib.dvlp_rw_tcgen05_supported(R, W, 256) == 1
+    for R, W, d in ((80, 32, 128), (80, 129, 256), (320, 64, 256), (200, 32, 256)):
+        assert lib.dvlp_rw_path(R, W, d, 1) == 0 and lib.dvlp_rw_tcgen05_supported(R, W, d) == 0, (R, W, d)
+    # the training workspace of a large shape holds its spills; the forward-only one does not
+    big = lib.dvlp_rw_workspace_bytes(64, 512, 288, 64, 256, _lib.BF16, 0)
+    small = lib.dvlp_rw_infer_workspace_bytes(64, 512, 288, 64, 256, _lib.BF16, 0)
+    assert 0 < small < big and big > 3 * 10 ** 9
+    # bf16 gradient output exists only where the small-shape finalisation serves the shape
+    assert lib.dvlp_rw_bwd_out_dtype_supported(0, 80, 32, 256, 20.0, _lib.BF16) == 1
+    assert lib.dvlp_rw_bwd_out_dtype_supported(0, 288, 64, 256, 20.0, _lib.BF16) == 0
+    assert lib.dvlp_rw_bwd_out_dtype_supported(0, 80, 32, 256, 50.0, _lib.BF16) == 0      # lambda beyond the tcgen05 bound
+    assert lib.dvlp_rw_bwd_out_dtype_supported(1, 80, 32, 256, 20.0, _lib.F32) == 1
+    z, one = C.c_void_p(0), C.c_void_p(256)
+    # grouped (multiple-choice) scoring
+    assert lib.dvlp_rw_grouped_workspace_bytes(64, 5, 240, 99, 256, _lib.BF16) > 0
+    assert lib.dvlp_rw_grouped_workspace_bytes(64, 5, 80, 32, 128, _lib.BF16) == 0
+    assert lib.dvlp_rw_scores_grouped_infer(z, z, z, z, 4, 5, 30, 99, 256, 20.0, 1, 1, z, z, 0, z) == -3
+    assert lib.dvlp_rw_scores_grouped_infer(one, one, one, one, 4, 0, 30, 99, 256, 20.0, 1, 1, one, one, 0, z) == -1
+    assert lib.dvlp_rw_scores_grouped_infer(one, one, one, one, 4, 5, 30, 99, 128, 20.0, 1, 1, one, one, 0, z) == -1
+    # projection heads
+    assert lib.dvlp_proj_workspace_bytes(100, 768, _lib.F32, 1) >= 100 * 768 * 2
+    assert lib.dvlp_proj_workspace_bytes(100, 700, _lib.F32, 1) == 0                        # K not a multiple of 64
+    assert lib.dvlp_proj_fwd(z, 0, 100, 768, 256, z, z, 1, z, z, 0, z) == -3
+    assert lib.dvlp_proj_fwd(one, 0, 100, 768, 128, one, z, 1, one, one, 0, z) == -1        # only 256 outputs
+    assert lib.dvlp_p2p_check(z, z) == -3
+    assert b"timed out" in lib.dvlp_error_string(-9)
+
+
+def test_projection_module_mirrors_reference_parameters():
+    """FusedProjection keeps nn.Linear's parameter names / shapes (model/model.py:40-43: Sequential(ReLU, Linear(768, 256)),
+    object_transformer.py:381: Linear(768, 256, bias=False)), so reference checkpoints load; CPU tensors are refused."""
+    from demovlp_b200.proj import FusedProjection
+    t = FusedProjection(768, 256, relu_in=True, bias=True)
+    v = FusedProjection(768, 256, relu_in=False, bias=False)
+    assert dict((k, tuple(p.shape)) for k, p in t.named_parameters()) == {"weight": (256, 768), "bias": (256,)}
+    assert dict((k, tuple(p.shape)) for k, p in v.named_parameters()) == {"weight": (256, 768)}
+    ref = torch.nn.Linear(768, 256)
+    t.load_state_dict(ref.state_dict())
+    with pytest.raises(RuntimeError):
+        t(torch.zeros(2, 5, 768))
