@@ -568,7 +568,8 @@ bool shape3(int R, int W, int d, Shape3* s) {
   t.NB = rp32 < rp48 ? 32 : 48;
   t.Rp = t.NB == 32 ? rp32 : rp48;
   t.nch = t.Rp / t.NB;
-  if (t.TPT * t.Rp > tf3::kMaxTab) return false;
+  // table of column norms kept between the sweeps; the dV' GEMM keeps one TMEM column per region (grad_gemm3.cu)
+  if (t.TPT * t.Rp > tf3::kMaxTab || t.Rp > 384) return false;
   if (s) *s = t;
   return true;
 }
