@@ -76,18 +76,29 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // Sum over the 32 lanes of v[c], c = 0..15: lane l ends with the total of column l & 15.
 // Lane bit b is paired with column bit b; the columns a lane still holds after a step are those whose
 // bit matches its own, so 16 -> 8 -> 4 -> 2 -> 1 values, then lanes l and l ^ 16 add up.
-__device__ __forceinline__ float lanes_to_columns16(float (&v)[16], int lane) {
+// The input array is left untouched (the first step writes into its own 8 registers: callers need no copy).
+__device__ __forceinline__ float lanes_to_columns16(const float (&v)[16], int lane) {
+  float r[8];
+  {
+    const bool up = (lane & 8) != 0;
 #pragma unroll
-  for (int h = 8; h >= 1; h >>= 1) {
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v[i] : v[i + 8];
+      const float keep = up ? v[i + 8] : v[i];
+      r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+#pragma unroll
+  for (int h = 4; h >= 1; h >>= 1) {
     const bool up = (lane & h) != 0;
 #pragma unroll
     for (int i = 0; i < h; ++i) {
-      const float send = up ? v[i] : v[i + h];
-      const float keep = up ? v[i + h] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+      const float send = up ? r[i] : r[i + h];
+      const float keep = up ? r[i + h] : r[i];
+      r[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
     }
   }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+  return r[0] + __shfl_xor_sync(0xffffffffu, r[0], 16);
 }
 
 template <int R>
@@ -359,13 +370,9 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       float thr2_cl;
       {
         const float nBl = nB * a.lam2;
-        float eb2[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          eB[c] = ex2(fmaf(leaky(x[c]), nBl, m2t_m));
-          eb2[c] = eB[c];
-        }
-        const float sumB = lanes_to_columns16(eb2, lane);
+        for (int c = 0; c < 16; ++c) eB[c] = ex2(fmaf(leaky(x[c]), nBl, m2t_m));
+        const float sumB = lanes_to_columns16(eB, lane);
         thr2_cl = a.focal ? sumB * (1.f / kW) : -1.f;
         if (lane < 16) s_thr[cl] = thr2_cl;
         __syncwarp();
@@ -382,12 +389,16 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
 #pragma unroll
           for (int e = 0; e < 4; e += 2) {
             const int c = c4 * 4 + e, p2 = c >> 1;
-            w1[p2] = pack_bf16(eA[c] > thr1 ? eA[c] : 0.f, eA[c + 1] > thr1 ? eA[c + 1] : 0.f);
-            w2[p2] = pack_bf16(eB[c] > tv[e] ? eB[c] : 0.f, eB[c + 1] > tv[e + 1] ? eB[c + 1] : 0.f);
-            num1 = fmaf(bf16_lo(w1[p2]), x[c], num1);
-            num1 = fmaf(bf16_hi(w1[p2]), x[c + 1], num1);
-            pn[c] = bf16_lo(w2[p2]) * x[c];
-            pn[c + 1] = bf16_hi(w2[p2]) * x[c + 1];
+            const float a0 = eA[c] > thr1 ? eA[c] : 0.f, a1 = eA[c + 1] > thr1 ? eA[c + 1] : 0.f;
+            const float b0 = eB[c] > tv[e] ? eB[c] : 0.f, b1 = eB[c + 1] > tv[e + 1] ? eB[c + 1] : 0.f;
+            w1[p2] = pack_bf16(a0, a1);
+            w2[p2] = pack_bf16(b0, b1);
+            // numerators from the fp32 values: the operand's bf16 rounding is a 2^-9 relative perturbation of single
+            // terms of a 20-80 term sum (cosine moves by ~1e-5) and unpacking it again costs two instructions per element
+            num1 = fmaf(a0, x[c], num1);
+            num1 = fmaf(a1, x[c + 1], num1);
+            pn[c] = b0 * x[c];
+            pn[c + 1] = b1 * x[c + 1];
           }
         }
         // (the Y GEMMs of tile k-1 have read U1 / U2: waited for in the deferred pass above)
