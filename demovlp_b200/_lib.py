@@ -44,6 +44,9 @@ SYMBOLS = {
     "dvlp_normsoftmax_fwd_bwd": (_i, [_p, _i, _i, _f, _p, _p, _p, _p]),
     "dvlp_proj_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "dvlp_proj_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _sz, _p]),
+    "dvlp_attn_small_supported": (_i, [_i, _i, _i]),
+    "dvlp_attn_small_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "dvlp_attn_small_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "dvlp_ranks_t2v": (_i, [_p, _i, _i, _p, _p]),
     "dvlp_ranks_v2t": (_i, [_p, _i, _i, _p, _p]),
     "dvlp_p2p_control_bytes": (_sz, []),

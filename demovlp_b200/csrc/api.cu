@@ -61,6 +61,10 @@ int run_p2p_sum_scalar(void* const*, int, int, const float*, float*, cudaStream_
 int run_p2p_reduce_scatter(void* const*, int, int, size_t, size_t, void*, int, cudaStream_t);
 int run_p2p_check(const void*, cudaStream_t);
 size_t proj_workspace_bytes(int M, int K, int in_dtype, int relu_in);
+int attn_small_supported(int I, int J, int d);
+int run_attn_small_fwd(const float*, const float*, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+int run_attn_small_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int,
+                       int, int, float*, float*, float*, cudaStream_t);
 int run_proj_fwd(const void* x, int in_dtype, int M, int K, const void* w_bf16, const float* bias, int relu_in, void* out,
                  char* ws, cudaStream_t st);
 // tcgen05 path: pair_fwd2.cu, pair_bwd2.cu, grad_gemm2.cu
@@ -552,6 +556,30 @@ int dvlp_proj_fwd(const void* x, int in_dtype, int M, int K, int N, const void* 
   int rc = device_ok();
   if (rc) return rc;
   return run_proj_fwd(x, in_dtype, M, K, w_bf16, bias, relu_in, out_bf16, (char*)workspace, (cudaStream_t)stream);
+}
+
+int dvlp_attn_small_supported(int I, int J, int d) { return attn_small_supported(I, J, d); }
+
+int dvlp_attn_small_fwd(const float* q, const float* k, const float* v, const float* mask, int B, int I, int J, int d,
+                        float* out, float* lse, void* stream) {
+  if (!q || !k || !v || !out) return DVLP_ERR_NULL_POINTER;
+  if (B <= 0 || !attn_small_supported(I, J, d)) return DVLP_ERR_BAD_SHAPE;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) return DVLP_ERR_MISALIGNED;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_attn_small_fwd(q, k, v, mask, B, I, J, out, lse, (cudaStream_t)stream);
+}
+
+int dvlp_attn_small_bwd(const float* q, const float* k, const float* v, const float* mask, const float* out,
+                        const float* lse, const float* d_out, int B, int I, int J, int d, float* d_q, float* d_k,
+                        float* d_v, void* stream) {
+  if (!q || !k || !v || !out || !lse || !d_out || !d_q || !d_k || !d_v) return DVLP_ERR_NULL_POINTER;
+  if (B <= 0 || !attn_small_supported(I, J, d)) return DVLP_ERR_BAD_SHAPE;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)d_out | (uintptr_t)d_q | (uintptr_t)d_k | (uintptr_t)d_v) & 15)
+    return DVLP_ERR_MISALIGNED;
+  int rc = device_ok();
+  if (rc) return rc;
+  return run_attn_small_bwd(q, k, v, mask, out, lse, d_out, B, I, J, d_q, d_k, d_v, (cudaStream_t)stream);
 }
 
 size_t dvlp_p2p_control_bytes(void) { return 4096; }

@@ -180,6 +180,23 @@ int dvlp_proj_fwd(const void* x, int in_dtype, int M, int K, int N, const void* 
                   void* out_bf16, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Masked attention over the short token sequences of the ObjectTransformer:
+ *   out = softmax(q k^T + mask, dim=-1) v       -- attn_mask of model/object_transformer.py:93-100, called by
+ * VarAttention.forward (:125-196) on (batch x heads) sequences (space: 30 x 31 tokens, time: 8 x 9, CLS: 1 x (1 + F R)).
+ *   q (B, I, d), k / v (B, J, d), mask (B, J) additive or NULL, out (B, I, d), lse (B, I) or NULL; all fp32, d = 64.
+ *   dvlp_attn_small_supported: 1 = tensor-core kernels (I, J <= 64; fp32 operands split into bf16 hi + lo parts, so the
+ *   result has fp32-class accuracy), 2 = single-query kernels (I == 1, J <= 1024), 0 = not served.
+ *   One CTA per sequence; q, k, v, out are touched once.  The backward needs `out` and `lse` of the forward and
+ *   overwrites d_q, d_k, d_v (no atomics: deterministic).
+ */
+int dvlp_attn_small_supported(int I, int J, int d);
+int dvlp_attn_small_fwd(const float* q, const float* k, const float* v, const float* mask, int B, int I, int J, int d,
+                        float* out, float* lse, void* stream);
+int dvlp_attn_small_bwd(const float* q, const float* k, const float* v, const float* mask, const float* out,
+                        const float* lse, const float* d_out, int B, int I, int J, int d, float* d_q, float* d_k,
+                        float* d_v, void* stream);
+
+/*
  * Retrieval ranks (model/metric.py).  sims is the (Nq, Nv) float64 matrix the
  * trainer builds (trainer/trainer_dist.py:369-385), rows = text queries.
  *   t2v (metric.py:22-66):  ranks[i] = #{ j : sims[i][j] > sims[i][gt(i)] },  gt(i) = i / (Nq / Nv)

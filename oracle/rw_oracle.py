@@ -251,3 +251,12 @@ def projection(tokens, weight, bias=None, relu_in=False):
     x = F.relu(tokens) if relu_in else tokens
     y = F.linear(x, weight, bias)
     return y[:, 0, ...], y[:, 1:, ...]
+
+
+def attn_mask(q, k, v, mask=None):
+    """Masked attention of the ObjectTransformer (test infrastructure): model/object_transformer.py:93-100 --
+    sim = einsum('b i d, b j d -> b i j'); sim += mask; softmax over j; einsum with v."""
+    sim = torch.einsum("bid,bjd->bij", q, k)
+    if mask is not None:
+        sim = sim + mask
+    return torch.einsum("bij,bjd->bid", sim.softmax(dim=-1), v)

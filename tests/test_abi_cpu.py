@@ -155,3 +155,16 @@ def test_projection_module_mirrors_reference_parameters():
     t.load_state_dict(ref.state_dict())
     with pytest.raises(RuntimeError):
         t(torch.zeros(2, 5, 768))
+
+
+def test_attention_entry_points_without_gpu():
+    lib = _lib.load()
+    assert lib.dvlp_attn_small_supported(30, 31, 64) == 1 and lib.dvlp_attn_small_supported(8, 9, 64) == 1
+    assert lib.dvlp_attn_small_supported(1, 241, 64) == 2
+    assert lib.dvlp_attn_small_supported(65, 31, 64) == 0 and lib.dvlp_attn_small_supported(30, 31, 32) == 0
+    z, one = C.c_void_p(0), C.c_void_p(256)
+    assert lib.dvlp_attn_small_fwd(z, z, z, z, 4, 30, 31, 64, z, z, z) == -3
+    assert lib.dvlp_attn_small_fwd(one, one, one, z, 4, 80, 31, 64, one, z, z) == -1
+    from demovlp_b200 import attention
+    with pytest.raises(RuntimeError):
+        attention.attn_mask(torch.zeros(2, 3, 64), torch.zeros(2, 4, 64), torch.zeros(2, 4, 64))
