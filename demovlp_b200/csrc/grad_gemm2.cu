@@ -37,7 +37,7 @@ struct Lay {
   static constexpr int XBYTES = MODE == MODE_V ? 4 * kTileBytes : 4 * CH;
   static constexpr int STAGE = NP * PBYTES + XBYTES;
   static constexpr int BARS = kStages * STAGE;
-  static constexpr int TMEMPTR = BARS + 8 * 8;
+  static constexpr int TMEMPTR = BARS + 10 * 8;
   static constexpr int kAlloc = TMEMPTR + 16;
   static_assert(STAGE % 1024 == 0 && X % 1024 == 0, "128-byte-swizzle tiles need 1 KB alignment");
   static_assert(kAlloc <= 232448, "shared memory budget");
@@ -47,6 +47,7 @@ struct Args {
   int Bv, Bt, tiles_per_video;
   int n_groups, steps_per_split;  // MODE_V: video groups x text-tile splits;  MODE_T: text-tile groups x video splits
   int accumulate;                 // 1: red.global.add into `out` (zeroed by the caller), 0: plain stores (one split)
+  int persistent;                 // 1: gridDim.x CTAs share the (group, K step) sequence evenly (stream-K), always accumulating
   long long text_rows;            // Bt * W: valid rows of dT'
   float* out;                     // MODE_V: dV' (Bv, R, d);  MODE_T: dT' (Bt*W, d)
 };
@@ -72,17 +73,29 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
   const uint32_t done = sbase + L::BARS + 8 * (2 * kStages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // this CTA's group of NP videos (MODE_V) / text tiles (MODE_T) and its K range
-  const int pr = blockIdx.x % a.n_groups, z = blockIdx.x / a.n_groups;
+  // Work of this CTA: a list of SEGMENTS, each = one group of NP videos (MODE_V) / text tiles (MODE_T) and a K range.
+  //   classic:    one segment, (group, split) from blockIdx
+  //   persistent: the (group, K step) sequence of the whole launch is cut into gridDim.x equal pieces (stream-K), so
+  //               that every SM gets the same number of K steps whatever the group count; a piece may span groups
   const int k_total = MODE == MODE_V ? a.tiles_per_video : a.Bv;
-  const int k0 = z * a.steps_per_split;
-  const int n_steps = max(0, min(a.steps_per_split, k_total - k0));
-  const int m0 = NP * pr;
-  const int n_mem = min(NP, (MODE == MODE_V ? a.Bv : a.tiles_per_video) - m0);    // members of this group (1 or 2)
+  long long pos0, pos1;
+  if (a.persistent) {
+    const long long total = (long long)a.n_groups * k_total;
+    pos0 = total * blockIdx.x / gridDim.x;
+    pos1 = total * (blockIdx.x + 1) / gridDim.x;
+  } else {
+    const int pr0 = blockIdx.x % a.n_groups, z0 = blockIdx.x / a.n_groups;
+    const int kb = z0 * a.steps_per_split;
+    const int ns = max(0, min(a.steps_per_split, k_total - kb));
+    pos0 = (long long)pr0 * k_total + kb;
+    pos1 = pos0 + ns;
+  }
+  const uint32_t accfree = sbase + L::BARS + 8 * (2 * kStages + 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapP); prefetch_tmap(&mapX);
     for (int s = 0; s < 2 * kStages + 1; ++s) mbar_init(sbase + L::BARS + 8 * s, 1);
+    mbar_init(accfree, 4);            // the four epilogue warps have read the accumulators of a segment
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -96,23 +109,32 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
 
   if (warp == 0) {
     if (elect_one()) {
-      for (int k = 0; k < n_steps; ++k) {
-        const int s = k % kStages, it = k / kStages;
-        if (it > 0) mbar_wait(empty(s), (it - 1) & 1);
-        const uint32_t st = sbase + s * L::STAGE;
-        const int kk = k0 + k;                            // text tile (MODE_V) / video (MODE_T) of this step
-        mbar_arrive_expect_tx(full(s), L::XBYTES + n_mem * L::PBYTES);
-        for (int h = 0; h < n_mem; ++h) {
-          const long long unit = MODE == MODE_V ? (long long)(m0 + h) * a.tiles_per_video + kk
-                                                : (long long)kk * a.tiles_per_video + (m0 + h);
-          for (int c = 0; c < NC; ++c)
-            tma_load_2d(st + L::P + h * L::PBYTES + c * kCh32, &mapP, c * 16, (int)(unit * kRows), full(s));
+      long long kk_glob = 0;                                  // ring position over all segments
+      for (long long pos = pos0; pos < pos1;) {
+        const int pr = (int)(pos / k_total), k0 = (int)(pos % k_total);
+        const int n_steps = (int)min((long long)(k_total - k0), pos1 - pos);
+        const int m0 = NP * pr;
+        const int n_mem = min(NP, (MODE == MODE_V ? a.Bv : a.tiles_per_video) - m0);
+        for (int k = 0; k < n_steps; ++k, ++kk_glob) {
+          const int s = (int)(kk_glob % kStages);
+          const long long it = kk_glob / kStages;
+          if (it > 0) mbar_wait(empty(s), (uint32_t)((it - 1) & 1));
+          const uint32_t st = sbase + s * L::STAGE;
+          const int kk = k0 + k;                            // text tile (MODE_V) / video (MODE_T) of this step
+          mbar_arrive_expect_tx(full(s), L::XBYTES + n_mem * L::PBYTES);
+          for (int h = 0; h < n_mem; ++h) {
+            const long long unit = MODE == MODE_V ? (long long)(m0 + h) * a.tiles_per_video + kk
+                                                  : (long long)kk * a.tiles_per_video + (m0 + h);
+            for (int c = 0; c < NC; ++c)
+              tma_load_2d(st + L::P + h * L::PBYTES + c * kCh32, &mapP, c * 16, (int)(unit * kRows), full(s));
+          }
+          if (MODE == MODE_V) {
+            for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * kTileBytes, &mapX, c * 64, kk * kRows, full(s));
+          } else {
+            for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * L::CH, &mapX, c * 64, kk * R, full(s));
+          }
         }
-        if (MODE == MODE_V) {
-          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * kTileBytes, &mapX, c * 64, kk * kRows, full(s));
-        } else {
-          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * L::CH, &mapX, c * 64, kk * R, full(s));
-        }
+        pos += n_steps;
       }
     }
   } else if (warp == 1) {
@@ -120,43 +142,60 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
     constexpr uint32_t idT = idesc_bf16(128, 256, 0, 1);     // P (K-major, M = words) x V (MN-major)
     const uint32_t hiK = desc_hi(1024);
     const uint32_t hi32 = ((256u >> 4) & 0x3FFF) | (1u << 14) | (6u << 29);   // 32-byte swizzle, 8-row groups 256 B apart
-    for (int k = 0; k < n_steps; ++k) {
-      const int s = k % kStages, it = k / kStages;
-      mbar_wait(full(s), it & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t st = sbase + s * L::STAGE;
-        for (int h = 0; h < n_mem; ++h) {
-          const uint32_t acc = tmem + h * 256;
-          const uint32_t pb = st + L::P + h * L::PBYTES;
-          if (MODE == MODE_V) {
-            // K = 128 words: P rows are the K rows of an MN-major operand whose M (regions) chunks are 4 KB apart;
-            // M = 128 reads past the R valid regions (into the next tile): those accumulator lanes are never stored
-            const uint32_t loX = desc_lo(st + L::X, kTileBytes);
-            const uint32_t loP = desc_lo(pb, kCh32);
+    long long kk_glob = 0;
+    int seg = 0;
+    for (long long pos = pos0; pos < pos1; ++seg) {
+      const int pr = (int)(pos / k_total), k0 = (int)(pos % k_total);
+      const int n_steps = (int)min((long long)(k_total - k0), pos1 - pos);
+      const int m0 = NP * pr;
+      const int n_mem = min(NP, (MODE == MODE_V ? a.Bv : a.tiles_per_video) - m0);
+      if (seg > 0) { mbar_wait(accfree, (uint32_t)((seg - 1) & 1)); tc_fence_after(); }   // the epilogue has drained the accumulators
+      for (int k = 0; k < n_steps; ++k, ++kk_glob) {
+        const int s = (int)(kk_glob % kStages);
+        const long long it = kk_glob / kStages;
+        mbar_wait(full(s), (uint32_t)(it & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = sbase + s * L::STAGE;
+          for (int h = 0; h < n_mem; ++h) {
+            const uint32_t acc = tmem + h * 256;
+            const uint32_t pb = st + L::P + h * L::PBYTES;
+            if (MODE == MODE_V) {
+              // K = 128 words: P rows are the K rows of an MN-major operand whose M (regions) chunks are 4 KB apart;
+              // M = 128 reads past the R valid regions (into the next tile): those accumulator lanes are never stored
+              const uint32_t loX = desc_lo(st + L::X, kTileBytes);
+              const uint32_t loP = desc_lo(pb, kCh32);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              mma_bf16_w(acc, loP + ((ks * 512) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idV, (k | ks) != 0);
-          } else {
-            // K = R regions: one 16-column chunk of P per K step
-            const uint32_t loX = desc_lo(st + L::X, L::CH);
-            const uint32_t loP = desc_lo(pb);
+              for (int ks = 0; ks < 8; ++ks)
+                mma_bf16_w(acc, loP + ((ks * 512) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idV, (k | ks) != 0);
+            } else {
+              // K = R regions: one 16-column chunk of P per K step
+              const uint32_t loX = desc_lo(st + L::X, L::CH);
+              const uint32_t loP = desc_lo(pb);
 #pragma unroll
-            for (int ks = 0; ks < NC; ++ks)
-              mma_bf16_w(acc, loP + ((ks * kCh32) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idT, (k | ks) != 0);
+              for (int ks = 0; ks < NC; ++ks)
+                mma_bf16_w(acc, loP + ((ks * kCh32) >> 4), hi32, loX + ((ks * 2048) >> 4), hiK, idT, (k | ks) != 0);
+            }
           }
+          tc_commit(empty(s));
+          if (k == n_steps - 1) tc_commit(done);
         }
-        tc_commit(empty(s));
-        if (k == n_steps - 1) tc_commit(done);
+        __syncwarp();
       }
-      __syncwarp();
+      pos += n_steps;
     }
   } else {
-    // epilogue: thread = accumulator row (TMEM lane quadrant = warp % 4)
+    // epilogue: thread = accumulator row (TMEM lane quadrant = warp % 4); one pass per segment
     const int q = warp & 3, row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    if (n_steps > 0) {
-      mbar_wait(done, 0);
+    int seg = 0;
+    for (long long pos = pos0; pos < pos1; ++seg) {
+      const int pr = (int)(pos / k_total), k0 = (int)(pos % k_total);
+      const int n_steps = (int)min((long long)(k_total - k0), pos1 - pos);
+      const int m0 = NP * pr;
+      const int n_mem = min(NP, (MODE == MODE_V ? a.Bv : a.tiles_per_video) - m0);
+      pos += n_steps;
+      mbar_wait(done, (uint32_t)(seg & 1));
       tc_fence_after();
       for (int h = 0; h < n_mem; ++h) {
         bool valid;
@@ -189,6 +228,10 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
           }
         }
       }
+      // the accumulators may be overwritten by the next segment
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accfree);
     }
   }
   tc_fence_before();
@@ -234,8 +277,28 @@ static int launch_mode(const CUtensorMap& mP, const CUtensorMap& mX, Args a, int
     DVLP_CUDA_OK(cudaFuncSetAttribute(k_grad_gemm2<R, MODE, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
     attr_once.done();
   }
-  // groups x K splits ~ one wave of CTAs
   a.n_groups = (n_members + NP - 1) / NP;
+  // Stream-K variant (DVLP_GG_PERSIST=1; off by default): one CTA per SM, each takes an equal share of the (group, K step)
+  // sequence, so the launch is a single full wave whatever the group count (512 video pairs on 148 SMs are 3.46 waves,
+  // 128 text-tile pairs leave 20 SMs idle).  MEASURED on B200 (round 2): 3.19 ms instead of 3.08 at config 3 on one GPU,
+  // 82 us instead of 73 at config 2 -- the GEMMs stream the P tiles from HBM (10.8 GB in 3.1 ms), a partial last wave
+  // costs nothing because the memory system is the limiter, while stream-K adds a memset and red.global epilogues.
+  static const int persist = [] { const char* e = getenv("DVLP_GG_PERSIST"); return e ? atoi(e) : 0; }();
+  if (persist) {
+    const long long total = (long long)a.n_groups * k_total;
+    int grid = (int)(total < sms ? total : sms);
+    a.persistent = 1;
+    a.steps_per_split = 0;
+    if (!a.accumulate) {
+      DVLP_CUDA_OK(cudaMemsetAsync(a.out, 0, out_bytes, st));
+      a.accumulate = 1;
+    }
+    k_grad_gemm2<R, MODE, NP><<<grid, kThreads, L::kAlloc, st>>>(mP, mX, a);
+    DVLP_LAUNCH_OK();
+    return DVLP_OK;
+  }
+  a.persistent = 0;
+  // groups x K splits ~ one wave of CTAs
   int splits = may_split ? sms / a.n_groups : 1;
   if (splits < 1) splits = 1;
   if (splits > k_total) splits = k_total;
