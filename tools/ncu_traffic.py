@@ -5,6 +5,7 @@ usage: ncu_traffic.py fwd=<rep> bwd_pair=<rep> grad_gemm=<rep> > profiles/ncu_tr
 import csv, io, json, subprocess, sys
 
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+TIME_US = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}
 out = {}
 for arg in sys.argv[1:]:
     key, rep = arg.split("=", 1)
@@ -17,7 +18,7 @@ for arg in sys.argv[1:]:
     for r in launches:            # a report may hold several launches (e.g. both gradient GEMM modes): add them up
         rd += float(r[col["dram__bytes_read.sum"]]) * UNIT[units[col["dram__bytes_read.sum"]]]
         wr += float(r[col["dram__bytes_write.sum"]]) * UNIT[units[col["dram__bytes_write.sum"]]]
-        dur += float(r[col["gpu__time_duration.sum"]])
+        dur += float(r[col["gpu__time_duration.sum"]]) * TIME_US.get(units[col["gpu__time_duration.sum"]], 1.0)
         names.append(r[col["Kernel Name"]].split("(")[0])
     out[key] = {"kernels": names, "dram_bytes_per_launch": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
                 "ncu_duration_us": round(dur, 1),
