@@ -88,3 +88,24 @@ def test_padded_backward_plan_matches_oracle(shape):
     assert (sc2 - sc.detach()).abs().max() < 1e-6
     assert rel_err(d_im, im.grad) < 1e-5
     assert rel_err(d_s, s.grad) < 1e-5
+
+
+@pytest.mark.parametrize("focal", ["equal", "prob"])
+@pytest.mark.parametrize("shape", [(3, 30, 20, 4, 32, 32), (2, 50, 9, 3, 64, 32), (2, 17, 9, 3, 48, 64), (2, 40, 33, 2, 40, 33)])
+def test_direct_form_algebra_of_the_large_shape_kernels_matches_oracle(shape, focal):
+    """The algebra pair_fwd3.cu / pair_bwd3.cu / grad_gemm3.cu evaluate: direct form of the i2t cosine
+    denominator (no video Gram matrix), the backward factored into G, F, column / row sums and the P / UD1 / C products,
+    zero padding with the real counts -- against the oracle's autograd in fp64."""
+    from tests import emul_direct
+    Bv, R, W, Bt, Rp, Wp = shape
+    b = synth.make_batch(max(Bv, Bt), R, W, 32, 11, 0.2)
+    im, s = b.im[:Bv].double(), b.s[:Bt].double()
+    imm, sm = b.im_mask[:Bv].double(), b.s_mask[:Bt].double()
+    ic, sc = im.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    want = O.pair_scores(ic, sc, imm, sm, focal=focal)
+    gs = torch.randn(Bv, Bt, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    (want * gs).sum().backward()
+    got, d_im, d_s = emul_direct.forward_backward_direct(im, s, imm, sm, gs, Rp=Rp, Wp=Wp, focal=(focal == "equal"))
+    assert (got - want.detach()).abs().max() < 1e-6
+    assert rel_err(d_im, ic.grad) < 1e-5
+    assert rel_err(d_s, sc.grad) < 1e-5
