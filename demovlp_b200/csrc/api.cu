@@ -289,7 +289,15 @@ static size_t workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype,
   if (Bv <= 0 || Bt <= 0 || R <= 0 || W <= 0 || d <= 0) return 0;
   int path = kPathGeneric;
   if (pick_path(impl, R, W, d, train, &path) != DVLP_OK) return 0;
-  return make_workspace(Bv, Bt, R, W, d, in_dtype, path, train).total;
+  size_t n = make_workspace(Bv, Bt, R, W, d, in_dtype, path, train).total;
+  // The size query does not know lambda: under DVLP_IMPL_AUTO a call with lambda beyond the tensor-core bound (40)
+  // is served by the generic kernels, so the workspace must be large enough for either path.
+  int eff = impl == DVLP_IMPL_AUTO ? g_default_impl.load() : impl;
+  if (eff == DVLP_IMPL_AUTO && path != kPathGeneric) {
+    const size_t g = make_workspace(Bv, Bt, R, W, d, in_dtype, kPathGeneric, train).total;
+    if (g > n) n = g;
+  }
+  return n;
 }
 size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl) {
   return workspace_bytes(Bv, Bt, R, W, d, in_dtype, impl, true);

@@ -127,7 +127,8 @@ def rw_scores_grouped(im, s, im_mask, s_mask, n_per_group, lam=20.0, focal_equal
         im, s = im.float(), s.float()
     dt = _lib.dtype_code(im)
     nbytes = lib.dvlp_rw_grouped_workspace_bytes(G, n_per_group, R, W, d, dt)
-    if nbytes == 0:         # generic kernels, one (1 x n_per_group) problem per group
+    if nbytes == 0 or not (0.0 < float(lam) <= 40.0):     # generic kernels, one (1 x n_per_group) problem per group
+        # (shapes outside the large-shape kernel, or lambda beyond the tensor-core kernels' fixed-maximum bound)
         rows = [rw_scores_fwd_raw(im[g:g + 1], s[g * n_per_group:(g + 1) * n_per_group], im_mask[g:g + 1],
                                   s_mask[g * n_per_group:(g + 1) * n_per_group], lam, focal_equal, "auto", train=False)[0]
                 for g in range(G)]

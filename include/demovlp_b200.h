@@ -77,7 +77,8 @@ uint64_t dvlp_launch_count(void);
 void dvlp_profile_enable(int on);
 int dvlp_profile_read(double* ms_host, int* counts_host);
 
-/* Bytes of scratch dvlp_rw_scores_fwd / dvlp_rw_scores_bwd need for this shape. */
+/* Bytes of scratch dvlp_rw_scores_fwd / dvlp_rw_scores_bwd need for this shape.  The query does not take lambda: under
+ * DVLP_IMPL_AUTO it covers both the tensor-core path and the fp32 path a lambda > 40 call is routed to. */
 size_t dvlp_rw_workspace_bytes(int Bv, int Bt, int R, int W, int d, int in_dtype, int impl);
 
 /*

@@ -673,3 +673,28 @@ def test_object_transformer_attention_vs_oracle(shape):
     qg2, kg2, vg2 = (t.cuda().requires_grad_(True) for t in (q, k, v))
     (A.attn_mask(qg2, kg2, vg2, mask.cuda() if mask is not None else None) * w.cuda()).sum().backward()
     assert torch.equal(kg2.grad, kg.grad) and torch.equal(vg2.grad, vg.grad) and torch.equal(qg2.grad, qg.grad)
+
+
+def test_large_lambda_and_mask_quirks_on_the_large_shape_path():
+    """(a) lambda_softmax beyond the tensor-core kernels' fixed-maximum bound (40) is served by the fp32 kernels and still
+    matches the reference arithmetic; an explicit impl="tcgen05" refuses it.  (b) the reference's mask quirks at a shape of
+    the large-shape kernels: float64 video mask (MSRVTT_dataset.py:522), cap_mask=None (loss.py:307-308: a mask of ones),
+    a fully masked video (a constant shift: behaves as unmasked)."""
+    b = synth.make_batch(6, 30, 99, 256, 3, mask_dtype=torch.float64)
+    d = dev(b)
+    im, s = d.im.to(torch.bfloat16), d.s.to(torch.bfloat16)
+    want = O.pair_scores(b.im, b.s, b.im_mask.float(), b.s_mask, lam=50.0, focal="equal")
+    got = ops.rw_scores(im, s, d.im_mask, d.s_mask, lam=50.0)
+    assert (got.cpu() - want).abs().max() < SCORE_TOL
+    with pytest.raises(RuntimeError):
+        ops.rw_scores(im, s, d.im_mask, d.s_mask, lam=50.0, impl="tcgen05")
+    a = ops.rw_scores(im, s, d.im_mask, d.s_mask)                       # float64 mask
+    c = ops.rw_scores(im, s, d.im_mask.float(), d.s_mask)
+    assert torch.equal(a, c)
+    none = ops.rw_scores(im, s, d.im_mask, None)
+    assert (none.cpu() - O.pair_scores(b.im, b.s, b.im_mask.float(), None)).abs().max() < SCORE_TOL
+    full = b.im_mask.float().clone()
+    full[2] = -100.0                                                     # video 2: every region masked
+    got = ops.rw_scores(im, s, full.cuda(), d.s_mask)
+    want = O.pair_scores(b.im, b.s, full, b.s_mask)
+    assert torch.isfinite(got).all() and (got.cpu() - want).abs().max() < SCORE_TOL
