@@ -482,26 +482,31 @@ def extras(dev):
             out[tag] = {"error": f"{type(ex).__name__}: {ex}"}
         torch.cuda.empty_cache()
 
-    # ---- config 5: one rank's share of the DiDeMo shape (64 videos x 512 texts, R = 288, W = 64), fwd + bwd
-    try:
-        Rr, Ww, bv, Bt = 288, 64, 64, 512
-        b = synth.make_batch(Bt, Rr, Ww, D, seed=4).to(dev)
-        im, s = b.im[:bv].to(torch.bfloat16).contiguous(), b.s.to(torch.bfloat16)
-        imm = b.im_mask[:bv].contiguous()
+    # ---- config 5: one rank's share of the DiDeMo shape (64 videos x 512 texts, R = 288, W = 64), fwd + bwd; and the
+    #      per-GPU batches the reference actually ships: pre-training (128 x 128, R = 30, W = 99,
+    #      configs/pt/o2t-cl-local-select-loss-cc.json) and fine-tuning (32 x 32, R = 240, W = 99, configs/ft/msrvtt_o2t-select.json)
+    for tag, (Rr, Ww, bv, Bt) in {"c5_rank_share": (288, 64, 64, 512), "reference_pretrain_shape": (30, 99, 128, 128),
+                                   "reference_finetune_shape": (240, 99, 32, 32)}.items():
+        try:
+            b = synth.make_batch(Bt, Rr, Ww, D, seed=4).to(dev)
+            im, s = b.im[:bv].to(torch.bfloat16).contiguous(), b.s.to(torch.bfloat16)
+            imm = b.im_mask[:bv].contiguous()
 
-        def fb():
-            sc, st = ops.rw_scores_fwd_raw(im, s, imm, b.s_mask, 20.0, 1, "auto")
-            part, dsc = ops.rwa_tail_raw(sc, 20.0, 0, Bt)
-            ops.rw_scores_bwd_raw(st, dsc)
+            def fb():
+                sc, st = ops.rw_scores_fwd_raw(im, s, imm, b.s_mask, 20.0, 1, "auto")
+                part, dsc = ops.rwa_tail_raw(sc, 20.0, 0, Bt)
+                ops.rw_scores_bwd_raw(st, dsc)
 
-        ms = timeit(fb, 3, warm=1)
-        pairs = bv * Bt
-        out["c5_rank_share"] = {"pairs": pairs, "regions": Rr, "words": Ww, "videos": bv, "texts": Bt, "fwd_bwd_ms": ms,
-                                "pair_scores_per_s": pairs / (ms * 1e-3),
-                                "algorithmic_tflops": 18 * Rr * Ww * D * pairs / (ms * 1e-3) / 1e12,
-                                "kernel_path": "tcgen05" if lib.dvlp_rw_tcgen05_supported(Rr, Ww, D) else "generic fp32 CUDA cores"}
-    except Exception as ex:
-        out["c5_rank_share"] = {"error": f"{type(ex).__name__}: {ex}"}
+            ms = timeit(fb, 3, warm=1)
+            pairs = bv * Bt
+            out[tag] = {"pairs": pairs, "regions": Rr, "words": Ww, "videos": bv, "texts": Bt, "fwd_bwd_ms": ms,
+                        "pair_scores_per_s": pairs / (ms * 1e-3),
+                        "algorithmic_tflops": 18 * Rr * Ww * D * pairs / (ms * 1e-3) / 1e12,
+                        "kernel_path": "tcgen05" if lib.dvlp_rw_tcgen05_supported(Rr, Ww, D) else "generic fp32 CUDA cores"}
+            del b, im, s
+        except Exception as ex:
+            out[tag] = {"error": f"{type(ex).__name__}: {ex}"}
+        torch.cuda.empty_cache()
     torch.cuda.empty_cache()
     return out
 
