@@ -15,7 +15,8 @@ IMPL_AUTO, IMPL_GENERIC, IMPL_TCGEN05 = 0, 1, 2
 _IMPL_NAMES = {"auto": IMPL_AUTO, "generic": IMPL_GENERIC, "tcgen05": IMPL_TCGEN05}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdemovlp_b200.so")
+# DVLP_LIB: a differently built copy of the same library (kernel experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("DVLP_LIB") or os.path.join(_HERE, "lib", "libdemovlp_b200.so")
 
 # every symbol include/demovlp_b200.h declares: (restype, argtypes)
 _p, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t

@@ -58,6 +58,48 @@ __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162flo
 __device__ __forceinline__ float leaky(float x) { return fmaxf(x, kLeaky * x); }
 __device__ __forceinline__ float leaky_grad(float x) { return x > 0.f ? 1.f : kLeaky; }
 
+// Packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 do two IEEE fp32 operations per issue slot; the results are
+// bit-identical to the scalar instructions).  The pair kernels are issue-bound on their fp32 elementwise work, so
+// adjacent columns of a thread are processed as pairs wherever both need the same operation.
+__device__ __forceinline__ unsigned long long f2_pack(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r) {
+  float2 a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 f2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 leaky2(float2 x) {
+  const float2 t = fmul2(x, f2(kLeaky));
+  return make_float2(fmaxf(x.x, t.x), fmaxf(x.y, t.y));
+}
+// 1.0f where a > b, else 0.0f (one FSET; a select against zero becomes a multiply by this mask, which
+// moves half of its cost from the half-rate ALU pipe to a packed multiply)
+__device__ __forceinline__ float gt_mask(float a, float b) {
+  float r;
+  asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 gt_mask2(float2 a, float2 b) { return make_float2(gt_mask(a.x, b.x), gt_mask(a.y, b.y)); }
+
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream
 // around the kernels of one slot.  Off by default; costs nothing when off.
 enum ProfSlot { kProfFwd = 0, kProfBwd = 1, kProfPrep = 2, kProfFinal = 3, kProfGG = 4, kProfSlots = 5 };

@@ -14,13 +14,18 @@
 // [word rows][region columns] bf16 tiles in the 32-byte-swizzle layout, written row-wise by their owners.
 // Besides the scores the kernel saves the per-query scalars the backward re-uses (rowv / colv, common.cuh).
 //
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 3 TMEM owner, warps 4.. compute
-// (warpgroup g = column chunk, warp q of the group = text slot = TMEM lane quadrant).
+// Warp roles: the compute warps come first (four per 16-column chunk g, one per text slot q = warp % 4 = TMEM lane
+// quadrant), the control warpgroup last (TMA producer, MMA issuer, -, TMEM owner).  The fp32 elementwise work runs on
+// packed pairs of adjacent columns (FFMA2 / FMUL2 / FADD2, common.cuh).  What bounds the kernel is the
+// dependency latency along each compute warp's own instruction stream - five warps per scheduler cannot cover it -
+// so the hot loop is kept free of local-memory spills (values parked in TMEM, saved scalars stored early).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace dvlp {
 using namespace ptx;
+
+extern void* g_trace_buffer;   // api.cu (dvlp_debug_set_trace)
 
 namespace tf2 {
 constexpr int kD = 256, kW = 32, kTPT = 4, kRows = 128;
@@ -28,7 +33,8 @@ constexpr int kTileBytes = 16384, kCh32 = 4096;
 
 template <int R>
 struct Lay {
-  static constexpr int NC = R / 16, NW = 4 * NC, kThreads = 128 * (1 + NC);
+  static constexpr int NC = R / 16, NW = 4 * NC;
+  static constexpr int kCtl = 4, kThreads = 32 * (kCtl + NW);   // one control warpgroup + NC compute warpgroups
   static constexpr int kVChunk = R * 128;
   static constexpr int V = 0;                       // 4 chunks (K = 256)
   static constexpr int GV = V + 4 * kVChunk;        // 2 chunks
@@ -53,7 +59,7 @@ struct Lay {
 enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE0, S_DONE1, U_READY, Y_DONE, kNumBars };
 
 // TMEM columns: two S buffers, Y1, Y2
-constexpr uint32_t cS0 = 0, cS1 = 96, cY1 = 192, cY2 = 288;
+constexpr uint32_t cS0 = 0, cS1 = 96, cY1 = 192, cY2 = 288, cPark = 384;   // cPark: leaky(x) parked during the deferred pass
 
 struct Args {
   int Bv, Bt, tiles_per_video;
@@ -63,7 +69,18 @@ struct Args {
   int focal;
   float* scores;
   float4 *rowv, *colv;    // per-unit query scalars for the backward; may be NULL (inference)
+  long long* trace;       // debug build (-DFWD2_TRACE) only: clock64 stamps of CTA 0, tools/trace_tiles.py
 };
+// trace slot layout: [role 0..4][tile 0..31][event 0..15]; roles: 1 = MMA warp, 2 = first compute warp, 3 = last one
+#ifdef FWD2_TRACE
+#define TR2(role, ev)                                                                                              \
+  do {                                                                                                             \
+    if (a.trace && blockIdx.x == 0 && lane == 0 && k < 32) a.trace[((role) * 32 + k) * 16 + (ev)] = clock64();      \
+  } while (0)
+#else
+#define TR2(role, ev) do { } while (0)
+#endif
+#define TRC(ev) do { if (cw == 0) TR2(2, ev); else if (cw == NW - 1) TR2(3, ev); } while (0)
 
 __device__ __forceinline__ uint32_t desc_hi32(uint32_t sbo_bytes) {      // 32-byte swizzle
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (6u << 29);
@@ -73,33 +90,37 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
   return r;
 }
-// Sum over the 32 lanes of v[c], c = 0..15: lane l ends with the total of column l & 15.
-// Lane bit b is paired with column bit b; the columns a lane still holds after a step are those whose
-// bit matches its own, so 16 -> 8 -> 4 -> 2 -> 1 values, then lanes l and l ^ 16 add up.
-// The input array is left untouched (the first step writes into its own 8 registers: callers need no copy).
-__device__ __forceinline__ float lanes_to_columns16(const float (&v)[16], int lane) {
-  float r[8];
+// Sum over the 32 lanes of the 16 columns held as 8 pairs (pair i = columns 2i, 2i+1): lane l ends with the total
+// of column l & 15.  Lane bit b is paired with column bit b; the columns a lane still holds after a step are those
+// whose bit matches its own, so 16 -> 8 -> 4 -> 2 -> 1 values, then lanes l and l ^ 16 add up.  The adds run as
+// packed pairs (FADD2).  The input array is left untouched.
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ float2 sel2(bool c, float2 a, float2 b) { return make_float2(c ? a.x : b.x, c ? a.y : b.y); }
+__device__ __forceinline__ float2 focal2(float2 e, float2 thr) { return fmul2(e, gt_mask2(e, thr)); }
+__device__ __forceinline__ float lanes_to_columns16(const float2 (&v)[8], int lane) {
+  float2 r[4];
   {
     const bool up = (lane & 8) != 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float send = up ? v[i] : v[i + 8];
-      const float keep = up ? v[i + 8] : v[i];
-      r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
+    for (int i = 0; i < 4; ++i) r[i] = fadd2(sel2(up, v[i + 4], v[i]), shfl_xor2(sel2(up, v[i], v[i + 4]), 8));
   }
+  {
+    const bool up = (lane & 4) != 0;
 #pragma unroll
-  for (int h = 4; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int i = 0; i < h; ++i) {
-      const float send = up ? r[i] : r[i + h];
-      const float keep = up ? r[i + h] : r[i];
-      r[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-    }
+    for (int i = 0; i < 2; ++i) r[i] = fadd2(sel2(up, r[i + 2], r[i]), shfl_xor2(sel2(up, r[i], r[i + 2]), 4));
   }
-  return r[0] + __shfl_xor_sync(0xffffffffu, r[0], 16);
+  {
+    const bool up = (lane & 2) != 0;
+    r[0] = fadd2(sel2(up, r[1], r[0]), shfl_xor2(sel2(up, r[0], r[1]), 2));
+  }
+  const bool up = (lane & 1) != 0;
+  const float t = (up ? r[0].y : r[0].x) + __shfl_xor_sync(0xffffffffu, up ? r[0].x : r[0].y, 1);
+  return t + __shfl_xor_sync(0xffffffffu, t, 16);
 }
+// the two bf16 halves of a packed word as an fp32 pair
+__device__ __forceinline__ float2 bf16_pair(uint32_t w) { return make_float2(bf16_lo(w), bf16_hi(w)); }
 
 template <int R>
 __global__ void __launch_bounds__(Lay<R>::kThreads, 1)
@@ -116,13 +137,18 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
   auto bar = [&](int i) { return sbase + L::BARS + 8 * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The warp scheduler prefers the highest warp id among its ready warps, so the control warps are the LAST
+  // warpgroup: a barrier the whole CTA waits behind (U_READY -> the Y GEMMs) is served at once instead of after the
+  // compute warps of that scheduler have run dry.  role: 0 TMA producer, 1 MMA issuer, 3 TMEM owner; -1 compute.
+  const int role = warp >= NW ? warp - NW : -1, cw = warp;
+  constexpr int gFin = NC - 1;                  // the warpgroup that writes the scores: the one the scheduler favours
   const long long u0 = a.total_units * blockIdx.x / gridDim.x;
   const long long u1 = a.total_units * (blockIdx.x + 1) / gridDim.x;
   const int n_tiles = (int)(u1 - u0);
   const int tpv = a.tiles_per_video;
   const int i0 = (int)(u0 / tpv), jt0 = (int)(u0 % tpv);
 
-  if (warp == 0 && lane == 0) {
+  if (role == 0 && lane == 0) {
     prefetch_tmap(&mapV); prefetch_tmap(&mapT); prefetch_tmap(&mapGV); prefetch_tmap(&mapGBD);
     for (int b = 0; b < kNumBars; ++b) {
       uint32_t cnt = 1;
@@ -131,7 +157,7 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     }
     fence_mbar_init();
   }
-  if (warp == 3) {
+  if (role == 3) {
     tmem_alloc(sbase + L::TMEMPTR, 512);
     tmem_relinquish();
   }
@@ -140,9 +166,11 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp < 4) {
+  if (role >= 0) {
+    // R = 80: the launch gives each of the 24 warps 80 registers; the control warps drop to 32 and the 20 compute
+    // warps take 88 out of the CTA's pool (4 x 48 released >= 20 x 8; 96 would not fit and never be granted)
     if (NC == 5) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-    if (warp == 0) {
+    if (role == 0) {
       // =============================== TMA producer ===============================
       if (elect_one()) {
         int i = i0, jt = jt0;
@@ -174,7 +202,7 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           if (++jt == tpv) { jt = 0; ++i; }
         }
       }
-    } else if (warp == 1) {
+    } else if (role == 1) {
       // ================================ MMA issuer ================================
       constexpr uint32_t idS = idesc_bf16(128, R), idY2 = idesc_bf16(128, R, 0, 1);
       constexpr uint32_t CH = L::kVChunk;
@@ -207,9 +235,12 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         // the new video's tile can only be loaded once tile k is finished
         const bool ahead = more && jt != 0;
         if (ahead) issue_S(k + 1, false);
+        TR2(1, 0);
         mbar_wait(bar(GBD_FULL), ph);
+        TR2(1, 1);
         mbar_wait(bar(U_READY), ph);
         tc_fence_after();
+        TR2(1, 2);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < NC; ++ks)
@@ -222,21 +253,21 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           tc_commit(bar(Y_DONE));
         }
         __syncwarp();
+        TR2(1, 3);
         if (more && !ahead) issue_S(k + 1, true);
       }
     }
   } else {
     // ============================ compute warps ============================
     if (NC == 5) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-    const int cw = warp - 4;
-    const int g = cw >> 2, q = cw & 3;          // column chunk, text slot / TMEM lane quadrant
+    const int g = cw >> 2, q = warp & 3;        // column chunk; text slot = TMEM lane quadrant of this warp (warp % 4)
     const int m = q * 32 + lane;                // word row of the tile
     const int cl = lane & 15;                   // column whose lane-reduced sums this lane ends up holding
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t sw = (uint32_t)((m >> 2) & 1) << 4;
     const uint32_t row_off = (uint32_t)g * kCh32 + (uint32_t)m * 32;
     const uint32_t seg0 = row_off + sw, seg1 = row_off + (16u ^ sw);
-    float* s_nal = reinterpret_cast<float*>(sgen + L::TAB + cw * 128);     // [16] nA * lam2 of this warp's columns
+    float* s_nal = reinterpret_cast<float*>(sgen + L::TAB + (g * 4 + q) * 128);     // [16] nA * lam2 of this warp's columns
     float* s_thr = s_nal + 16;                                               // [16] focal threshold of the t2i direction
     const float* s_beta = reinterpret_cast<const float*>(sgen + L::BETA);
     const float* s_m2t = reinterpret_cast<const float*>(sgen + L::M2T);
@@ -247,157 +278,201 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     int vloads = 0, i = i0, jt = jt0;
     // The last pass of a tile (Gram-form denominators, which need the Y GEMMs) is deferred into the next
     // iteration, after that tile's first pass: the tensor-core round trip hides under it.  Carried state:
-    float num1_p = 0.f, num2_p = 0.f, nA_p = 0.f, thr2_p = 0.f, nB_p = 0.f, thr1_p = 0.f;
-    int i_p = 0, j_p = 0;
-    // deferred pass 3 of tile kp (Gram-form denominators, t2i cosines); returns this thread's D1 row partial.
-    // `par` = parity of the iteration it runs in (selects the exchange buffers)
-    auto deferred_pass = [&](int kp, uint32_t par) -> float {
-      float D1p = 0.f;
+    // (the norms / thresholds the backward re-uses are stored in the tile's own iteration, the halves that need the
+    //  denominators one iteration later: they are not carried in registers)
+    float num1_p = 0.f, num2_p = 0.f;
+    long long sidx_p = -1;                      // element of the score matrix tile k-1 of this warp writes; -1: padded text
+    // deferred pass 3 of tile kp (Gram-form denominators, t2i cosines); deferred_a returns this thread's D1 row
+    // partial.  `par` = parity of the iteration it runs in (selects the exchange buffers)
+    // Split in two so that the TMEM round trips overlap: both Y tiles are requested before the one wait, and the
+    // caller re-requests its parked x / leaky(x) between the halves, under the lane reduction of the second.
+    float2 yd[8];                               // u2 * Y2 of tile kp between the halves
+    auto deferred_a = [&](int kp) -> float {
       mbar_wait(bar(Y_DONE), kp & 1);
       tc_fence_after();
-      uint32_t uw[8];                           // this thread's row segment of U1, then U2 (tile kp, still in place)
-      float y[16];
-      ld_shared_v4(sbase + L::U1 + seg0, uw[0], uw[1], uw[2], uw[3]);
-      ld_shared_v4(sbase + L::U1 + seg1, uw[4], uw[5], uw[6], uw[7]);
-      tmem_ld16(tmem + cY1 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
+      float2 y1[8];
+      tmem_ld16(tmem + cY1 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y1));
+      tmem_ld16(tmem + cY2 + lane_off + g * 16, reinterpret_cast<uint32_t*>(yd));
+      uint32_t u1w[8], u2w[8];                  // this thread's row segments of U1 / U2 (tile kp, still in place)
+      ld_shared_v4(sbase + L::U1 + seg0, u1w[0], u1w[1], u1w[2], u1w[3]);
+      ld_shared_v4(sbase + L::U1 + seg1, u1w[4], u1w[5], u1w[6], u1w[7]);
+      ld_shared_v4(sbase + L::U2 + seg0, u2w[0], u2w[1], u2w[2], u2w[3]);
+      ld_shared_v4(sbase + L::U2 + seg1, u2w[4], u2w[5], u2w[6], u2w[7]);
       tmem_ld_wait();
+      float2 D1a = f2(0.f), D1b = f2(0.f);
 #pragma unroll
-      for (int p2 = 0; p2 < 8; ++p2) {
-        D1p = fmaf(bf16_lo(uw[p2]), y[2 * p2], D1p);
-        D1p = fmaf(bf16_hi(uw[p2]), y[2 * p2 + 1], D1p);
+      for (int p2 = 0; p2 < 8; p2 += 2) {
+        D1a = ffma2(bf16_pair(u1w[p2]), y1[p2], D1a);
+        D1b = ffma2(bf16_pair(u1w[p2 + 1]), y1[p2 + 1], D1b);
       }
-      ld_shared_v4(sbase + L::U2 + seg0, uw[0], uw[1], uw[2], uw[3]);
-      ld_shared_v4(sbase + L::U2 + seg1, uw[4], uw[5], uw[6], uw[7]);
-      tmem_ld16(tmem + cY2 + lane_off + g * 16, reinterpret_cast<uint32_t*>(y));
-      tmem_ld_wait();
 #pragma unroll
-      for (int p2 = 0; p2 < 8; ++p2) {
-        y[2 * p2] *= bf16_lo(uw[p2]);
-        y[2 * p2 + 1] *= bf16_hi(uw[p2]);
-      }
-      const float D2_cl = lanes_to_columns16(y, lane);
+      for (int p2 = 0; p2 < 8; ++p2) yd[p2] = fmul2(yd[p2], bf16_pair(u2w[p2]));
+      return (D1a.x + D1b.x) + (D1a.y + D1b.y);
+    };
+    auto deferred_b = [&](int kp, uint32_t par) {
+      const float D2_cl = lanes_to_columns16(yd, lane);
       // t2i: cos2 of this warp's 16 (text, region) queries, summed over the regions (model/loss.py:326-327)
       const float rden2 = D2_cl > 1e-30f ? rsqrtf(D2_cl) : 0.f;
       float cos2 = num2_p * rden2;
       if (a.colv && lane < 16)
-        a.colv[((size_t)(u0 + kp) * kTPT + q) * R + g * 16 + cl] = make_float4(nA_p, thr2_p, rden2, cos2);
+        reinterpret_cast<float2*>(a.colv + ((size_t)(u0 + kp) * kTPT + q) * R + g * 16 + cl)[1] = make_float2(rden2, cos2);
       cos2 += __shfl_xor_sync(0xffffffffu, cos2, 8);
       cos2 += __shfl_xor_sync(0xffffffffu, cos2, 4);
       cos2 += __shfl_xor_sync(0xffffffffu, cos2, 2);
       cos2 += __shfl_xor_sync(0xffffffffu, cos2, 1);
       if (lane == 0) s_t2i[(par * NC + g) * 4 + q] = cos2;
-      return D1p;
     };
-    // i2t cosine of every word of tile kp (row totals n1 / d1 from the exchange), the pair score: warpgroup 0 only
+    // i2t cosine of every word of tile kp (row totals n1 / d1 from the exchange), the pair score: warpgroup gFin only
     auto finish_tile = [&](int kp, uint32_t par, float n1, float d1) {
       const float rden1 = d1 > 1e-30f ? rsqrtf(d1) : 0.f;
       float cs = n1 * rden1;
-      if (a.rowv) a.rowv[(size_t)(u0 + kp) * kRows + m] = make_float4(nB_p, thr1_p, rden1, cs);
+      if (a.rowv) reinterpret_cast<float2*>(a.rowv + (size_t)(u0 + kp) * kRows + m)[1] = make_float2(rden1, cs);
       cs = warp_sum(cs);                        // mean over the 32 words of text q (model/loss.py:318)
-      if (lane == 0 && j_p < a.Bt) {
+      if (lane == 0 && sidx_p >= 0) {
         float t2i = 0.f;
 #pragma unroll
         for (int gg = 0; gg < NC; ++gg) t2i += s_t2i[(par * NC + gg) * 4 + q];
-        a.scores[(size_t)i_p * a.Bt + j_p] = cs * (1.f / kW) + t2i * (1.f / R);
+        a.scores[sidx_p] = cs * (1.f / kW) + t2i * (1.f / R);
       }
     };
 
     for (int k = 0; k < n_tiles; ++k) {
       const uint32_t ph = k & 1;
-      float x[16], eA[16];
-      float ssB = 0.f, sumA = 0.f;
+      TRC(0);
+      float2 x[8], l[8], eA[8];                 // pair p = columns 2p, 2p+1: x = raw alpha beta, l = leaky(x)
       if (k == 0 || jt == 0) { mbar_wait(bar(V_FULL), vloads & 1); ++vloads; }
       mbar_wait(bar(VEC_FULL), ph);
       const float beta_m = s_beta[m], m2t_m = s_m2t[m];
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(VEC_FREE));
+      TRC(1);
       // ------------- pass 0: S = raw alpha beta, the query-axis l2 norm of the i2t direction (model/loss.py:238) -------------
       mbar_wait(bar(S_DONE0 + ph), (k >> 1) & 1);
       tc_fence_after();
       tmem_ld16(tmem + (ph ? cS1 : cS0) + lane_off + g * 16, reinterpret_cast<uint32_t*>(x));
       tmem_ld_wait();
-      float nA_cl;
+      TRC(2);
+      float nA_cl, ssB;
       {
-        float sq[16];
+        float2 sq[8], ssB2 = f2(0.f);
+        const float2 bb = f2(beta_m);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const float4 al = s_alpha4[c4];
-          const float av[4] = {al.x, al.y, al.z, al.w};
+          const float2 av[2] = {make_float2(al.x, al.y), make_float2(al.z, al.w)};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c4 * 4 + e;
-            x[c] *= av[e] * beta_m;
-            const float l = leaky(x[c]);
-            sq[c] = l * l;
-            ssB += sq[c];
+          for (int e = 0; e < 2; ++e) {
+            const int p = c4 * 2 + e;
+            x[p] = fmul2(x[p], fmul2(av[e], bb));
+            l[p] = leaky2(x[p]);
+            sq[p] = fmul2(l[p], l[p]);
+            ssB2 = fadd2(ssB2, sq[p]);
           }
         }
+        ssB = ssB2.x + ssB2.y;
         const float ssA = lanes_to_columns16(sq, lane);        // sum over the 32 words of this text, column cl
         nA_cl = 1.f / (sqrtf(ssA) + kEps);
         if (lane < 16) s_nal[cl] = nA_cl * a.lam2;
       }
+      TRC(3);
       // ------------- deferred pass 3 of tile k-1 (its Y GEMMs ran under the pass above) -------------
+      // x and leaky(x) sit out the pass in TMEM (x over the raw similarities it came from, which nobody reads again;
+      // leaky(x) in spare columns): two stores and two loads instead of 32 registers at the kernel's pressure peak
       float D1p = 0.f;
-      if (k > 0) D1p = deferred_pass(k - 1, ph);
+      const uint32_t t_x = tmem + (ph ? cS1 : cS0) + lane_off + g * 16, t_l = tmem + cPark + lane_off + g * 16;
+      if (k > 0) {
+        tmem_st16(t_x, reinterpret_cast<const uint32_t*>(x));
+        tmem_st16(t_l, reinterpret_cast<const uint32_t*>(l));
+        D1p = deferred_a(k - 1);
+        tmem_st_wait();
+        tmem_ld16(t_x, reinterpret_cast<uint32_t*>(x));
+        tmem_ld16(t_l, reinterpret_cast<uint32_t*>(l));
+        deferred_b(k - 1, ph);
+        tmem_ld_wait();
+      }
+      TRC(4);
       // ------------- pass 1a: exponentials of the i2t direction (need only the lane-reduced norm) -------------
       __syncwarp();                             // s_nal
+      float sumA;
+      {
+        float2 sumA2 = f2(0.f);
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const float4 nl = reinterpret_cast<const float4*>(s_nal)[c4];
-        const float4 mv = s_m2v4[c4];
-        const float nv[4] = {nl.x, nl.y, nl.z, nl.w}, mvv[4] = {mv.x, mv.y, mv.z, mv.w};
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 nl = reinterpret_cast<const float4*>(s_nal)[c4];
+          const float4 mv = s_m2v4[c4];
+          const float2 nv[2] = {make_float2(nl.x, nl.y), make_float2(nl.z, nl.w)};
+          const float2 mvv[2] = {make_float2(mv.x, mv.y), make_float2(mv.z, mv.w)};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = c4 * 4 + e;
-          eA[c] = ex2(fmaf(leaky(x[c]), nv[e], mvv[e]));
-          sumA += eA[c];
+          for (int e = 0; e < 2; ++e) {
+            const int p = c4 * 2 + e;
+            const float2 t = ffma2(l[p], nv[e], mvv[e]);
+            eA[p] = make_float2(ex2(t.x), ex2(t.y));
+            sumA2 = fadd2(sumA2, eA[p]);
+          }
         }
+        sumA = sumA2.x + sumA2.y;
       }
       // ------------- the one exchange of row partials per tile (the NC warps that share this text slot) -------------
       s_part[(ph * NC + g) * kRows + m] = make_float4(ssB, sumA, num1_p, D1p);
+      TRC(5);
       named_bar_sync(1 + q, 32 * NC);
+      TRC(6);
       float totB = 0.f, totA = 0.f, n1 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int gg = 0; gg < NC; ++gg) {
         const float4 pt = s_part[(ph * NC + gg) * kRows + m];
         totB += pt.x; totA += pt.y; n1 += pt.z; d1 += pt.w;
       }
-      if (k > 0 && g == 0) finish_tile(k - 1, ph, n1, d1);
-      // ------------- pass 1b: the t2i direction, focal thresholds -------------
+      if (k > 0 && g == gFin) finish_tile(k - 1, ph, n1, d1);
+      // ------------- pass 2a: focal-selected u1 (bf16) and its numerator: the i2t exponentials die here -------------
+      // (the focal select e > thr ? e : 0 is a multiply by the 1.0 / 0.0 compare mask; e is finite.  Numerators use the
+      //  bf16 values the MMAs see, so that numerator and Gram-form denominator stay consistent: taking the fp32 values
+      //  instead moved the scores by 2.5e-4 instead of 1.5e-4 and tripled the rank flips of the 1000 x 1000 eval matrix)
       const float nB = 1.f / (sqrtf(totB) + kEps);
       const float thr1 = a.focal ? totA * (1.f / R) : -1.f;    // keep e iff e * R > sum_r e  (model/loss.py:280-282)
-      float eB[16];
+      uint32_t w1[8], w2[8];
+      float num1;
+      {
+        float2 num12 = f2(0.f);
+        const float2 th1 = f2(thr1);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const float2 u1 = focal2(eA[p], th1);
+          w1[p] = pack_bf16(u1.x, u1.y);
+          num12 = ffma2(bf16_pair(w1[p]), x[p], num12);
+        }
+        num1 = num12.x + num12.y;
+      }
+      TRC(7);
+      // ------------- pass 1b: the t2i direction, focal thresholds -------------
+      float2 eB[8];
       float thr2_cl;
       {
-        const float nBl = nB * a.lam2;
+        const float2 nBl = f2(nB * a.lam2), mt = f2(m2t_m);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) eB[c] = ex2(fmaf(leaky(x[c]), nBl, m2t_m));
+        for (int p = 0; p < 8; ++p) {
+          const float2 t = ffma2(l[p], nBl, mt);
+          eB[p] = make_float2(ex2(t.x), ex2(t.y));
+        }
         const float sumB = lanes_to_columns16(eB, lane);
         thr2_cl = a.focal ? sumB * (1.f / kW) : -1.f;
         if (lane < 16) s_thr[cl] = thr2_cl;
         __syncwarp();
       }
-      // ------------- pass 2: focal-selected u (bf16), operand tiles, numerators -------------
-      float num1 = 0.f;
+      TRC(8);
+      // ------------- pass 2b: focal-selected u2, operand tiles -------------
       {
-        uint32_t w1[8], w2[8];
-        float pn[16];
+        float2 pn[8];
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const float4 th = reinterpret_cast<const float4*>(s_thr)[c4];
-          const float tv[4] = {th.x, th.y, th.z, th.w};
+          const float2 tv[2] = {make_float2(th.x, th.y), make_float2(th.z, th.w)};
 #pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const int c = c4 * 4 + e, p2 = c >> 1;
-            w1[p2] = pack_bf16(eA[c] > thr1 ? eA[c] : 0.f, eA[c + 1] > thr1 ? eA[c + 1] : 0.f);
-            w2[p2] = pack_bf16(eB[c] > tv[e] ? eB[c] : 0.f, eB[c + 1] > tv[e + 1] ? eB[c + 1] : 0.f);
-            // numerators with the bf16 values the MMAs see: numerator and Gram-form denominator stay consistent (taking
-            // the fp32 values instead saves 32 instructions per tile but moved the scores by 2.5e-4 instead of 1.5e-4
-            // and tripled the end-to-end rank flips of the 1000 x 1000 eval matrix: measured, rejected)
-            num1 = fmaf(bf16_lo(w1[p2]), x[c], num1);
-            num1 = fmaf(bf16_hi(w1[p2]), x[c + 1], num1);
-            pn[c] = bf16_lo(w2[p2]) * x[c];
-            pn[c + 1] = bf16_hi(w2[p2]) * x[c + 1];
+          for (int e = 0; e < 2; ++e) {
+            const int p = c4 * 2 + e;
+            const float2 u2 = focal2(eB[p], tv[e]);
+            w2[p] = pack_bf16(u2.x, u2.y);
+            pn[p] = fmul2(bf16_pair(w2[p]), x[p]);
           }
         }
         // (the Y GEMMs of tile k-1 have read U1 / U2: waited for in the deferred pass above)
@@ -409,19 +484,25 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(U_READY));
+        TRC(9);
         num2_p = lanes_to_columns16(pn, lane);                 // under the Y GEMMs
       }
-      num1_p = num1; nA_p = nA_cl; thr2_p = thr2_cl; nB_p = nB; thr1_p = thr1;
-      i_p = i; j_p = jt * kTPT + q;
+      TRC(10);
+      num1_p = num1;
+      if (a.colv && lane < 16)
+        reinterpret_cast<float2*>(a.colv + ((size_t)(u0 + k) * kTPT + q) * R + g * 16 + cl)[0] = make_float2(nA_cl, thr2_cl);
+      if (a.rowv && g == gFin) reinterpret_cast<float2*>(a.rowv + (size_t)(u0 + k) * kRows + m)[0] = make_float2(nB, thr1);
+      sidx_p = (jt * kTPT + q < a.Bt) ? (long long)i * a.Bt + (jt * kTPT + q) : -1;
       if (++jt == tpv) { jt = 0; ++i; }
     }
     // ------------- the last tile's deferred pass -------------
     {
       const uint32_t par = n_tiles & 1;
-      const float D1p = deferred_pass(n_tiles - 1, par);
+      const float D1p = deferred_a(n_tiles - 1);
+      deferred_b(n_tiles - 1, par);
       s_part[(par * NC + g) * kRows + m] = make_float4(0.f, 0.f, num1_p, D1p);
       named_bar_sync(1 + q, 32 * NC);
-      if (g == 0) {
+      if (g == gFin) {
         float n1 = 0.f, d1 = 0.f;
 #pragma unroll
         for (int gg = 0; gg < NC; ++gg) {
@@ -436,7 +517,7 @@ k_pair_fwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) tmem_dealloc(tmem, 512);
+  if (role == 3) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------ host side
@@ -487,6 +568,7 @@ static int launch(const void* vb, const void* tb, int Bv, int Bt, float lambda, 
   a.lam2 = lambda * kLog2e; a.focal = focal; a.scores = scores;
   a.rowv = save ? (float4*)(ws + Lw.rowv) : nullptr;
   a.colv = save ? (float4*)(ws + Lw.colv) : nullptr;
+  a.trace = (long long*)g_trace_buffer;
   int dev = 0, sms = 148;
   DVLP_CUDA_OK(cudaGetDevice(&dev));
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -21,8 +21,13 @@ else:   # pair_bwd2.cu
 
 
 def main():
+    global EV_MMA, EV_GRP
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     which = sys.argv[2] if len(sys.argv) > 2 else "bwd"
+    if which == "fwd":   # pair_fwd2.cu built with -DFWD2_TRACE (tools/variants.sh pair_fwd2 trace "-DFWD2_TRACE")
+        EV_MMA = ["S ahead issued", "Gbd full", "U ready", "Y issued"]
+        EV_GRP = ["loop top", "vec full", "S loaded", "pass0 done", "deferred done", "1a done", "bar passed", "2a done",
+                  "1b done", "U arrive", "num2 done"]
     lib = _lib.load()
     lib.dvlp_debug_set_trace.argtypes = [C.c_void_p]
     lib.dvlp_debug_set_trace.restype = None
@@ -42,7 +47,7 @@ def main():
     lib.dvlp_debug_set_trace(None)
     t = trace.cpu().view(5, 32, 16)
     t0 = int(t[t > 0].min())
-    for k in (2, 3, 4):
+    for k in (6, 7, 8):
         base = int(t[2, k, 0]) if t[2, k, 0] > 0 else t0
         print(f"--- tile {k} (cycles relative to group A start of this tile; tile period "
               f"{int(t[2, k + 1, 0] - t[2, k, 0])} cycles)")
