@@ -76,8 +76,8 @@ enum Tab { T_NAL = 0, T_THR2, T_ALPHA, T_M2V,   // phase 1: nA lam2, thr2, alpha
            kNumTab };
 static_assert(kNumTab <= 12, "768 bytes per warp");
 
-enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE, U_READY, Y_DONE, DGT_STAGED, DG_DONE, P_READY,
-           P_STORED, UD_READY, kNumBars };
+enum Bar { V_FULL = 0, T_FULL, GBD_FULL, VEC_FULL, VEC_FREE, S_DONE, U_READY, Y_DONE, DG_DONE, P_READY, P_STORED, UD_READY,
+           kNumBars };
 
 // TMEM columns
 constexpr uint32_t cS = 0, cY1 = 96, cY2 = 192, cDGV = 288, cDGT = 384;
@@ -151,7 +151,6 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     for (int b = 0; b < kNumBars; ++b) {
       uint32_t cnt = 1;
       if (b == VEC_FREE || b == U_READY || b == P_READY || b == UD_READY) cnt = NW;
-      if (b == DGT_STAGED) cnt = 8;
       mbar_init(bar(b), cnt);
     }
     fence_mbar_init();
@@ -185,8 +184,8 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           if (k > 0) mbar_wait(bar(DG_DONE), pp);
           mbar_arrive_expect_tx(bar(T_FULL), 4 * kTileBytes);
           for (int c = 0; c < 4; ++c) tma_load_2d(sbase + L::T + c * kTileBytes, &mapT, c * 64, jt * kRows, bar(T_FULL));
-          // block-diagonal text Gram tile: its buffer staged the dG^T block of the previous tile (bulk reduce read it)
-          if (k > 0) mbar_wait(bar(P_STORED), pp);
+          // block-diagonal text Gram tile: the Y2 GEMM of the previous tile has read it
+          if (k > 0) mbar_wait(bar(Y_DONE), pp);
           mbar_arrive_expect_tx(bar(GBD_FULL), 2 * kTileBytes);
           for (int c = 0; c < 2; ++c) tma_load_2d(sbase + L::GBD + c * kTileBytes, &mapGBD, c * 64, jt * kRows, bar(GBD_FULL));
           if (k == 0 || jt == 0) {
@@ -269,24 +268,16 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         TR2(1, 4);
       }
     } else if (role == 2) {
-      // ====== stores: the bf16 gradient tile P of each unit (TMA tile store) and its dG^T block (bulk add) ======
+      // ====== stores: the bf16 gradient tile P of each unit (TMA tile store) ======
       if (elect_one()) {
-        int jt = jt0;
         for (int k = 0; k < n_tiles; ++k) {
           mbar_wait(bar(P_READY), k & 1);
           const int row = (int)((u0 + k) * kRows);
 #pragma unroll
           for (int c = 0; c < NC; ++c) tma_store_2d(&mapP, sbase + L::U1 + c * kCh32, c * 16, row);
           bulk_commit();
-          // dG^T: 128 rows x 32 fp32 staged row-major in the (idle) Gbd buffer; only the rows of real texts are added
-          mbar_wait(bar(DGT_STAGED), k & 1);
-          int nt = a.Bt - jt * kTPT;
-          nt = nt > kTPT ? kTPT : nt;
-          bulk_reduce_add_f32(a.dgt + (size_t)jt * kRows * kW, sbase + L::GBD, (uint32_t)nt * kW * kW * 4);
-          bulk_commit();
-          bulk_wait_read0();                 // U1 may take the next tile's u, the Gbd buffer the next Gram tile
+          bulk_wait_read0();                 // U1 may take the next tile's u
           mbar_arrive(bar(P_STORED));
-          if (++jt == tpv) jt = 0;
         }
         bulk_wait_all();
       }
@@ -318,6 +309,37 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       return v;
     };
     float gs_next = load_g(i, jt);
+    // The Gram gradients of a tile leave TMEM one tile late, in the shadow of the next tile's Y GEMMs (the warps would
+    // only wait there): dG^T block of this warp's text straight from registers with red.global (16-byte chunks of a row
+    // XOR-swizzled with the row index - the permutation the global dG^T buffer has always kept and epilogue.cu undoes,
+    // dgt_swz), dG^V rows after the last tile of a video.  Both are read before this warp signals UD_READY, i.e.
+    // before the next dG GEMMs can touch the accumulators.
+    int jt_prev = 0, i_prev = 0;
+    bool last_prev = false;
+    auto flush_gram = [&]() {
+      tc_fence_after();
+      if (g < 2 && jt_prev * kTPT + q < a.Bt) {
+        float v[16];
+        tmem_ld16(tmem + cDGT + lane_off + q * 32 + g * 16, reinterpret_cast<uint32_t*>(v));
+        tmem_ld_wait();
+        float* dst = a.dgt + ((size_t)jt_prev * kRows + m) * kW;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          red_add_v4(dst + (((g * 4 + c) ^ (lane & 7)) << 2), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+      if (last_prev && q * 32 < R) {
+        // dG^V rows (TMEM lanes = regions), this warpgroup's 16 columns
+        float v[16];
+        tmem_ld16(tmem + cDGV + lane_off + g * 16, reinterpret_cast<uint32_t*>(v));
+        tmem_ld_wait();
+        if (m < R) {
+          float* dst = a.dgv + ((size_t)i_prev * R + m) * R + g * 16;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) red_add_v4(dst + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+      }
+      tc_fence_before();
+    };
     for (int k = 0; k < n_tiles; ++k) {
       const uint32_t ph = k & 1;
       const bool last_of_video = (k == n_tiles - 1) || (jt == tpv - 1);
@@ -392,6 +414,7 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(U_READY));
+      if (k > 0) flush_gram();                  // Gram gradients of tile k-1
       // the u dD operand tiles of the Gram-gradient GEMMs are formed while the Y GEMMs run
       {
         const float2 dDA = f2(-0.5f * c1A * kapA);
@@ -538,40 +561,11 @@ k_pair_bwd2(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(bar(P_READY));
       TRC(9);
 
-      // ------------------------------ Gram gradients leave TMEM ------------------------------
-      tc_fence_after();
-      if (g < 2) {
-        // dG^T block of this text (rows = this word), 16 of its 32 columns per warpgroup: staged in shared memory
-        // (row-major, exactly the global layout) and added to global memory by ONE bulk reduce of the store warp
-        float v[16];
-        tmem_ld16(tmem + cDGT + lane_off + q * 32 + g * 16, reinterpret_cast<uint32_t*>(v));
-        tmem_ld_wait();
-        // 16-byte chunks of a row are XOR-swizzled with the row index (conflict-free stores); the global dG^T
-        // buffer keeps the same permutation and epilogue.cu undoes it (dgt_swz)
-        const uint32_t dst = sbase + L::GBD + (uint32_t)m * (kW * 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          st_shared_v4(dst + (((uint32_t)(g * 4 + c) ^ (uint32_t)(lane & 7)) << 4), __float_as_uint(v[4 * c]),
-                       __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(DGT_STAGED));
-      }
-      if (last_of_video && q * 32 < R) {
-        // dG^V rows (TMEM lanes = regions), this warpgroup's 16 columns
-        float v[16];
-        tmem_ld16(tmem + cDGV + lane_off + g * 16, reinterpret_cast<uint32_t*>(v));
-        tmem_ld_wait();
-        if (m < R) {
-          float* dst = a.dgv + ((size_t)i * R + m) * R + g * 16;
-#pragma unroll
-          for (int c = 0; c < 16; c += 4) red_add_v4(dst + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
-        }
-      }
-      tc_fence_before();
+      jt_prev = jt; i_prev = i; last_prev = last_of_video;
       TRC(10);
       if (++jt == tpv) { jt = 0; ++i; }
     }
+    if (n_tiles > 0) flush_gram();              // (the last tile's dG GEMMs: DG_DONE was waited for in its phase 3)
   }
 
   tc_fence_before();
