@@ -7,6 +7,11 @@
 //
 //   MODE_V   dV'[i]  (R x d)   = sum_jt P[i, jt]^T T_jt      one CTA per video, K loop over text tiles
 //   MODE_T   dT'[jt] (128 x d) = sum_i  P[i, jt]   V_i       one CTA per (text tile, video split)
+//   MODE_VT  dV'[i]^T (d x R)  = sum_jt T_jt^T P[i, jt]      MODE_V with the roles of the operands swapped: M = d (two
+//            halves of 128 lanes), N = the R regions of BOTH videos of the CTA (their P tiles are adjacent in shared
+//            memory, so one MMA covers them), K = 128 words.  MODE_V pads its M = R rows to 128 lanes - 37 % of its
+//            tensor work at R = 80, and ncu shows the launch 66 % tensor-active - the transposed form executes exactly
+//            the algorithmic products.  The epilogue writes one dV' row element per lane (128-byte runs per warp).
 //
 // T / V are the RAW bf16 embeddings (the alpha/beta factors are already in P).  The accumulator
 // (128 lanes x 256 fp32 columns) stays in TMEM for the whole K loop, operands arrive by TMA into a
@@ -25,16 +30,16 @@ using namespace ptx;
 namespace gg2 {
 constexpr int kD = 256, kRows = 128, kThreads = 192;
 constexpr int kTileBytes = 16384, kCh32 = 4096;
-enum { MODE_V = 0, MODE_T = 1 };
+enum { MODE_V = 0, MODE_T = 1, MODE_VT = 2 };   // MODE_VT: dV' in the transposed orientation (below), same work split as MODE_V
 
 template <int R, int MODE, int NP>
 struct Lay {
   static constexpr int NC = R / 16;                                   // 16-column chunks of the P tile
   static constexpr int CH = R * 128;                                  // one 64-column chunk of an R-row tile
-  static constexpr int kStages = NP == 2 ? 2 : (MODE == MODE_V ? 2 : 3);
+  static constexpr int kStages = NP == 2 ? 2 : (MODE == MODE_T ? 3 : 2);
   static constexpr int PBYTES = NC * kCh32;
   static constexpr int P = 0, X = NP * PBYTES;                        // NP P tiles share one X operand
-  static constexpr int XBYTES = MODE == MODE_V ? 4 * kTileBytes : 4 * CH;
+  static constexpr int XBYTES = MODE == MODE_T ? 4 * CH : 4 * kTileBytes;
   static constexpr int STAGE = NP * PBYTES + XBYTES;
   static constexpr int BARS = kStages * STAGE;
   static constexpr int TMEMPTR = BARS + 10 * 8;
@@ -77,7 +82,8 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
   //   classic:    one segment, (group, split) from blockIdx
   //   persistent: the (group, K step) sequence of the whole launch is cut into gridDim.x equal pieces (stream-K), so
   //               that every SM gets the same number of K steps whatever the group count; a piece may span groups
-  const int k_total = MODE == MODE_V ? a.tiles_per_video : a.Bv;
+  constexpr bool kByVideo = MODE != MODE_T;       // groups are videos, the K loop runs over text tiles
+  const int k_total = kByVideo ? a.tiles_per_video : a.Bv;
   long long pos0, pos1;
   if (a.persistent) {
     const long long total = (long long)a.n_groups * k_total;
@@ -114,7 +120,7 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
         const int pr = (int)(pos / k_total), k0 = (int)(pos % k_total);
         const int n_steps = (int)min((long long)(k_total - k0), pos1 - pos);
         const int m0 = NP * pr;
-        const int n_mem = min(NP, (MODE == MODE_V ? a.Bv : a.tiles_per_video) - m0);
+        const int n_mem = min(NP, (kByVideo ? a.Bv : a.tiles_per_video) - m0);
         for (int k = 0; k < n_steps; ++k, ++kk_glob) {
           const int s = (int)(kk_glob % kStages);
           const long long it = kk_glob / kStages;
@@ -123,12 +129,12 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
           const int kk = k0 + k;                            // text tile (MODE_V) / video (MODE_T) of this step
           mbar_arrive_expect_tx(full(s), L::XBYTES + n_mem * L::PBYTES);
           for (int h = 0; h < n_mem; ++h) {
-            const long long unit = MODE == MODE_V ? (long long)(m0 + h) * a.tiles_per_video + kk
-                                                  : (long long)kk * a.tiles_per_video + (m0 + h);
+            const long long unit = kByVideo ? (long long)(m0 + h) * a.tiles_per_video + kk
+                                            : (long long)kk * a.tiles_per_video + (m0 + h);
             for (int c = 0; c < NC; ++c)
               tma_load_2d(st + L::P + h * L::PBYTES + c * kCh32, &mapP, c * 16, (int)(unit * kRows), full(s));
           }
-          if (MODE == MODE_V) {
+          if (kByVideo) {
             for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * kTileBytes, &mapX, c * 64, kk * kRows, full(s));
           } else {
             for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * L::CH, &mapX, c * 64, kk * R, full(s));
@@ -148,7 +154,7 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
       const int pr = (int)(pos / k_total), k0 = (int)(pos % k_total);
       const int n_steps = (int)min((long long)(k_total - k0), pos1 - pos);
       const int m0 = NP * pr;
-      const int n_mem = min(NP, (MODE == MODE_V ? a.Bv : a.tiles_per_video) - m0);
+      const int n_mem = min(NP, (kByVideo ? a.Bv : a.tiles_per_video) - m0);
       if (seg > 0) { mbar_wait(accfree, (uint32_t)((seg - 1) & 1)); tc_fence_after(); }   // the epilogue has drained the accumulators
       for (int k = 0; k < n_steps; ++k, ++kk_glob) {
         const int s = (int)(kk_glob % kStages);
@@ -157,7 +163,21 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
         tc_fence_after();
         if (elect_one()) {
           const uint32_t st = sbase + s * L::STAGE;
-          for (int h = 0; h < n_mem; ++h) {
+          if (MODE == MODE_VT) {
+            // A = T_jt^T: d is the contiguous (M) direction, 64-column chunks 16 KB apart, one accumulator per half of d;
+            // B = the P tiles of the CTA's videos: regions contiguous (N), 16-column chunks 4 KB apart and adjacent
+            // across the videos; K = 16 words per instruction
+            const uint32_t loX = desc_lo(st + L::X, kTileBytes);
+            const uint32_t loP = desc_lo(st + L::P, kCh32);
+            const uint32_t id = n_mem == 2 ? idesc_bf16(128, 2 * R, 1, 1) : idesc_bf16(128, R, 1, 1);
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                mma_bf16_w(tmem + half * 256, loX + ((half * 2 * kTileBytes + ks * 2048) >> 4), hiK, loP + ((ks * 512) >> 4),
+                           hi32, id, (k | ks) != 0);
+          }
+          for (int h = 0; MODE != MODE_VT && h < n_mem; ++h) {
             const uint32_t acc = tmem + h * 256;
             const uint32_t pb = st + L::P + h * L::PBYTES;
             if (MODE == MODE_V) {
@@ -193,11 +213,31 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
       const int pr = (int)(pos / k_total), k0 = (int)(pos % k_total);
       const int n_steps = (int)min((long long)(k_total - k0), pos1 - pos);
       const int m0 = NP * pr;
-      const int n_mem = min(NP, (MODE == MODE_V ? a.Bv : a.tiles_per_video) - m0);
+      const int n_mem = min(NP, (kByVideo ? a.Bv : a.tiles_per_video) - m0);
       pos += n_steps;
       mbar_wait(done, (uint32_t)(seg & 1));
       tc_fence_after();
-      for (int h = 0; h < n_mem; ++h) {
+      if (MODE == MODE_VT) {
+        // lane = column of dV' (half * 128 + row), TMEM column = (video of the CTA, region) = consecutive dV' rows
+        const int ncols = n_mem * R;
+        for (int half = 0; half < 2; ++half) {
+          float* dst = a.out + (size_t)m0 * R * kD + half * 128 + row;
+#pragma unroll 1
+          for (int c = 0; c < ncols; c += 16) {
+            float v[16];
+            tmem_ld16(tmem + half * 256 + lane_off + c, reinterpret_cast<uint32_t*>(v));
+            tmem_ld_wait();
+            if (a.accumulate) {
+#pragma unroll
+              for (int x = 0; x < 16; ++x) atomicAdd(dst + (size_t)(c + x) * kD, v[x]);
+            } else {
+#pragma unroll
+              for (int x = 0; x < 16; ++x) dst[(size_t)(c + x) * kD] = v[x];
+            }
+          }
+        }
+      }
+      for (int h = 0; MODE != MODE_VT && h < n_mem; ++h) {
         bool valid;
         float* dst;
         if (MODE == MODE_V) {
@@ -338,7 +378,7 @@ static int launch(const void* vb_all, const void* tb, int v0, int Bv, int Bt, in
   a.out = (float*)(ws + Lw.dvh) + (size_t)v0 * R * kD; a.accumulate = 0;
   const size_t dv_bytes = (size_t)Bv * R * kD * 4;
   // (a chunk of few videos: split the K loop over CTAs so that the launch still fills the GPU)
-  rc = pair ? launch_mode<R, MODE_V, 2>(mP, mT, a, Bv, tiles, sms, true, dv_bytes, st)
+  rc = pair ? launch_mode<R, MODE_VT, 2>(mP, mT, a, Bv, tiles, sms, true, dv_bytes, st)
             : launch_mode<R, MODE_V, 1>(mP, mT, a, Bv, tiles, sms, 2 * Bv <= sms, dv_bytes, st);
   if (rc) return rc;
   a.out = (float*)(ws + Lw.dth); a.accumulate = 1;
