@@ -279,6 +279,178 @@ k_grad_gemm2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
   if (warp == 1) tmem_dealloc(tmem, 256 * NP);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Paired CTAs (two accumulators, long K loops), fine-grained ring.  With whole (text tile / video) steps the 2-stage
+// ring of k_grad_gemm2 has one 80 - 104 KB stage in flight while the other is consumed: ncu shows the launches half
+// tensor-active, waiting for the fill (HBM / L2 latency + the per-SM fill rate).  Here a ring slot is a K SLICE of a
+// step - 32 words of a text tile (MODE_VT: 10 + 16 KB, 8 slots) or 16 regions of a video (MODE_T: 8 + 8 KB, 12
+// slots) - so ~180 KB are in flight per SM instead of ~90.  Same work split, operands and results as k_grad_gemm2.
+template <int R, int MODE>
+struct LayF {
+  static_assert(MODE == MODE_VT || MODE == MODE_T, "paired modes only");
+  static constexpr int NC = R / 16, NP = 2;
+  static constexpr int kSub = MODE == MODE_VT ? 4 : NC;               // slices per step
+  static constexpr int PSL = MODE == MODE_VT ? 1024 : kCh32;          // one P chunk slice: 32 rows x 32 B | 128 rows x 32 B
+  static constexpr int PBYTES = MODE == MODE_VT ? NC * PSL : PSL;     // per video / text tile and slice
+  static constexpr int XCH = MODE == MODE_VT ? 4096 : 2048;           // 64-column chunk of the X slice: 32 | 16 rows x 128 B
+  static constexpr int P = 0, X = (NP * PBYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE = X + 4 * XCH;
+  static constexpr int kStages = (200 * 1024) / STAGE < 12 ? (200 * 1024) / STAGE : 12;
+  static constexpr int BARS = kStages * STAGE;
+  static constexpr int TMEMPTR = BARS + (2 * kStages + 2) * 8;
+  static constexpr int kAlloc = TMEMPTR + 16;
+  static_assert(STAGE % 1024 == 0, "128-byte-swizzle tiles need 1 KB alignment");
+  static_assert(kAlloc <= 232448, "shared memory budget");
+};
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+k_grad_gemm2f(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapX, Args a) {
+  using L = LayF<R, MODE>;
+  constexpr int kStages = L::kStages, NC = L::NC, NP = 2, kSub = L::kSub;
+  constexpr bool kByVideo = MODE == MODE_VT;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (sbase & 1023u) __trap();
+  volatile uint32_t* s_tmem = (volatile uint32_t*)(smem_raw + L::TMEMPTR);
+  auto full = [&](int s) { return sbase + L::BARS + 8 * s; };
+  auto empty = [&](int s) { return sbase + L::BARS + 8 * (kStages + s); };
+  const uint32_t done = sbase + L::BARS + 8 * (2 * kStages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int k_total = kByVideo ? a.tiles_per_video : a.Bv;
+  const int pr = blockIdx.x % a.n_groups, z0 = blockIdx.x / a.n_groups;
+  const int k0 = z0 * a.steps_per_split;
+  const int n_steps = max(0, min(a.steps_per_split, k_total - k0));
+  const int m0 = NP * pr;
+  const int n_mem = min(NP, (kByVideo ? a.Bv : a.tiles_per_video) - m0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapP); prefetch_tmap(&mapX);
+    for (int s = 0; s < 2 * kStages + 1; ++s) mbar_init(sbase + L::BARS + 8 * s, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(sbase + L::TMEMPTR, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int cnt = 0;
+      for (int k = 0; k < n_steps; ++k) {
+        const int kk = k0 + k;                              // text tile (MODE_VT) / video (MODE_T) of this step
+        for (int j = 0; j < kSub; ++j, ++cnt) {
+          const int s = cnt % kStages, it = cnt / kStages;
+          if (it > 0) mbar_wait(empty(s), (uint32_t)((it - 1) & 1));
+          const uint32_t st = sbase + s * L::STAGE;
+          mbar_arrive_expect_tx(full(s), 4 * L::XCH + n_mem * L::PBYTES);
+          for (int h = 0; h < n_mem; ++h) {
+            if (kByVideo) {                                   // rows 32 j .. 32 j + 31 of every region chunk
+              const long long unit = (long long)(m0 + h) * a.tiles_per_video + kk;
+              for (int c = 0; c < NC; ++c)
+                tma_load_2d(st + L::P + (h * NC + c) * L::PSL, &mapP, c * 16, (int)(unit * kRows) + j * 32, full(s));
+            } else {                                          // region chunk j, all 128 rows
+              const long long unit = (long long)kk * a.tiles_per_video + (m0 + h);
+              tma_load_2d(st + L::P + h * L::PSL, &mapP, j * 16, (int)(unit * kRows), full(s));
+            }
+          }
+          const int xrow = kByVideo ? kk * kRows + j * 32 : kk * R + j * 16;
+          for (int c = 0; c < 4; ++c) tma_load_2d(st + L::X + c * L::XCH, &mapX, c * 64, xrow, full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idT = idesc_bf16(128, 256, 0, 1);     // P (K-major, M = words) x V (MN-major)
+    const uint32_t idVT = n_mem == 2 ? idesc_bf16(128, 2 * R, 1, 1) : idesc_bf16(128, R, 1, 1);
+    const uint32_t hiK = desc_hi(1024);
+    const uint32_t hi32 = ((256u >> 4) & 0x3FFF) | (1u << 14) | (6u << 29);   // 32-byte swizzle, 8-row groups 256 B apart
+    int cnt = 0;
+    for (int k = 0; k < n_steps; ++k) {
+      for (int j = 0; j < kSub; ++j, ++cnt) {
+        const int s = cnt % kStages, it = cnt / kStages;
+        mbar_wait(full(s), (uint32_t)(it & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = sbase + s * L::STAGE;
+          const uint32_t loX = desc_lo(st + L::X, L::XCH);
+          if (MODE == MODE_VT) {
+            // A = 32 words of T_jt^T (M = d: 64-column chunks 4 KB apart, one accumulator per half of d), B = the same
+            // words of the P tiles (N = regions: 16-column chunks 1 KB apart, adjacent across the videos)
+            const uint32_t loP = desc_lo(st + L::P, L::PSL);
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                mma_bf16_w(tmem + half * 256, loX + ((half * 2 * L::XCH + ks * 2048) >> 4), hiK, loP + ((ks * 512) >> 4), hi32,
+                           idVT, (k | j | ks) != 0);
+          } else {
+            for (int h = 0; h < n_mem; ++h)
+              mma_bf16_w(tmem + h * 256, desc_lo(st + L::P + h * L::PSL), hi32, loX, hiK, idT, (k | j) != 0);
+          }
+          tc_commit(empty(s));
+          if (k == n_steps - 1 && j == kSub - 1) tc_commit(done);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (n_steps > 0) {
+    // epilogue (as k_grad_gemm2): thread = accumulator lane (TMEM lane quadrant = warp % 4)
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (MODE == MODE_VT) {
+      const int ncols = n_mem * R;
+      for (int half = 0; half < 2; ++half) {
+        float* dst = a.out + (size_t)m0 * R * kD + half * 128 + row;
+#pragma unroll 1
+        for (int c = 0; c < ncols; c += 16) {
+          float v[16];
+          tmem_ld16(tmem + half * 256 + lane_off + c, reinterpret_cast<uint32_t*>(v));
+          tmem_ld_wait();
+          if (a.accumulate) {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) atomicAdd(dst + (size_t)(c + x) * kD, v[x]);
+          } else {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) dst[(size_t)(c + x) * kD] = v[x];
+          }
+        }
+      }
+    } else {
+      for (int h = 0; h < n_mem; ++h) {
+        const long long grow = (long long)(m0 + h) * kRows + row;
+        const bool valid = grow < a.text_rows;
+        float* dst = a.out + (size_t)grow * kD;
+#pragma unroll 1
+        for (int c = 0; c < kD; c += 32) {
+          float v[32];
+          tmem_ld16(tmem + h * 256 + lane_off + c, reinterpret_cast<uint32_t*>(v));
+          tmem_ld16(tmem + h * 256 + lane_off + c + 16, reinterpret_cast<uint32_t*>(v) + 16);
+          tmem_ld_wait();
+          if (valid) {
+            if (a.accumulate) {
+#pragma unroll
+              for (int x = 0; x < 32; x += 4) red_add_v4(dst + c + x, v[x], v[x + 1], v[x + 2], v[x + 3]);
+            } else {
+#pragma unroll
+              for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4*>(dst + c + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -353,6 +525,32 @@ static int launch_mode(const CUtensorMap& mP, const CUtensorMap& mX, Args a, int
   return DVLP_OK;
 }
 
+// the fine-grained-ring kernel for the paired modes (groups x K splits ~ one wave of CTAs, like launch_mode)
+template <int R, int MODE>
+static int launch_fine(const CUtensorMap& mP, const CUtensorMap& mX, Args a, int n_members, int k_total, int sms,
+                       size_t out_bytes, cudaStream_t st) {
+  using L = LayF<R, MODE>;
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
+    DVLP_CUDA_OK(cudaFuncSetAttribute(k_grad_gemm2f<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
+    attr_once.done();
+  }
+  a.n_groups = (n_members + 1) / 2;
+  a.persistent = 0;
+  int splits = sms / a.n_groups;
+  if (splits < 1) splits = 1;
+  if (splits > k_total) splits = k_total;
+  a.steps_per_split = (k_total + splits - 1) / splits;
+  splits = (k_total + a.steps_per_split - 1) / a.steps_per_split;
+  if (!a.accumulate && splits > 1) {       // split partial sums need a zeroed output
+    DVLP_CUDA_OK(cudaMemsetAsync(a.out, 0, out_bytes, st));
+    a.accumulate = 1;
+  }
+  k_grad_gemm2f<R, MODE><<<a.n_groups * splits, kThreads, L::kAlloc, st>>>(mP, mX, a);
+  DVLP_LAUNCH_OK();
+  return DVLP_OK;
+}
+
 // videos [v0, v0 + Bv): their P tiles sit at the start of the (chunk-sized) P buffer; dV' rows of the range are written,
 // dT' accumulates over the range
 template <int R>
@@ -378,6 +576,17 @@ static int launch(const void* vb_all, const void* tb, int v0, int Bv, int Bt, in
   a.out = (float*)(ws + Lw.dvh) + (size_t)v0 * R * kD; a.accumulate = 0;
   const size_t dv_bytes = (size_t)Bv * R * kD * 4;
   // (a chunk of few videos: split the K loop over CTAs so that the launch still fills the GPU)
+  // DVLP_GG_FINE = 0: the paired CTAs with whole-step stages (k_grad_gemm2) instead of the fine-grained ring
+  static const int fine = [] { const char* e = getenv("DVLP_GG_FINE"); return e ? atoi(e) : 1; }();
+  if (pair && fine) {
+    CUtensorMap mP32, mT32, mV16;            // K-slice boxes: 32 words of a P chunk / text tile, 16 regions of a video
+    if ((rc = make_map(&mP32, ws + Lw.pa, (uint64_t)units * kRows, R, 32, 16, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+    if ((rc = make_map(&mT32, tb, (uint64_t)Bt * W, kD, 32))) return rc;
+    if ((rc = make_map(&mV16, vb, (uint64_t)Bv * R, kD, 16))) return rc;
+    if ((rc = launch_fine<R, MODE_VT>(mP32, mT32, a, Bv, tiles, sms, dv_bytes, st))) return rc;
+    a.out = (float*)(ws + Lw.dth); a.accumulate = 1;
+    return launch_fine<R, MODE_T>(mP, mV16, a, tiles, Bv, sms, 0, st);
+  }
   rc = pair ? launch_mode<R, MODE_VT, 2>(mP, mT, a, Bv, tiles, sms, true, dv_bytes, st)
             : launch_mode<R, MODE_V, 1>(mP, mT, a, Bv, tiles, sms, 2 * Bv <= sms, dv_bytes, st);
   if (rc) return rc;

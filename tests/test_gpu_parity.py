@@ -306,6 +306,32 @@ def test_tcgen05_gradients_ragged_text_tiles(shape):
         assert rel_err(y.grad.float().cpu(), sc.grad) < GRAD_TOL
 
 
+@pytest.mark.parametrize("shape", [(3, 80, 512), (5, 48, 509)])
+def test_paired_gradient_gemms_odd_video_count(shape):
+    """From 128 text tiles on grad_gemm2.cu keeps two accumulators per CTA and contracts dV' in the transposed
+    orientation (one MMA over the regions of both videos): an odd video count leaves the last CTA with a single
+    video (N = R instead of 2 R), few videos make the launch split its K loop (atomic partial sums), and 509 texts
+    leave a ragged last text tile.  Gradients against the oracle's autograd (1e-2 relative)."""
+    Bv, R, Bt = shape
+    b = synth.make_batch(Bt, R, 32, 256, seed=29)
+    im = b.im[:Bv].to(torch.bfloat16)
+    s = b.s[:Bt].to(torch.bfloat16)
+    imm, sm = b.im_mask[:Bv].contiguous(), b.s_mask[:Bt].contiguous()
+    w = torch.randn(Bv, Bt, generator=torch.Generator().manual_seed(6))
+    ic = im.float().clone().requires_grad_(True)
+    sc = s.float().clone().requires_grad_(True)
+    (O.pair_scores(ic, sc, imm, sm, focal="equal") * w).sum().backward()
+    x = im.cuda().requires_grad_(True)
+    y = s.cuda().requires_grad_(True)
+    got = ops.rw_scores(x, y, imm.cuda(), sm.cuda(), focal_equal=True, impl="tcgen05")
+    (got * w.cuda()).sum().backward()
+    assert torch.isfinite(x.grad).all() and torch.isfinite(y.grad).all()
+    assert rel_err(x.grad.float().cpu(), ic.grad) < GRAD_TOL
+    assert rel_err(y.grad.float().cpu(), sc.grad) < GRAD_TOL
+    for i in range(Bv):                         # every video on its own: the single-video CTA must not be diluted
+        assert rel_err(x.grad[i].float().cpu(), ic.grad[i]) < GRAD_TOL
+
+
 def test_sim_matrix_bf16_tensor_core_path():
     """bf16 CLS embeddings of width 256 take the mma.sync kernels (sim_mma.cu): exact products, fp32 norms,
     gradients written in bf16."""

@@ -9,7 +9,12 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg,", "sm__inst_executed.
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum,", "dram__bytes_write.sum,", "launch__registers_per_thread,",
         "lts__t_bytes.sum,", "smsp__inst_executed.sum,", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "lts__t_sectors_op_red.sum,", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+        "lts__t_sectors_op_red.sum,", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        # the shared-memory data pipe: LSU side (LDS / STS / SHFL) and tensor-core operand fetch
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum,", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum,",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 for h, v in zip(hdr, val):
     if any((h + ",").startswith(w) or h == w.rstrip(",") for w in want):
         print(f"{h} = {v}")
