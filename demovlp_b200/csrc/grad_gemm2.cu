@@ -568,10 +568,12 @@ static int launch(const void* vb_all, const void* tb, int v0, int Bv, int Bt, in
   DVLP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   Args a{};
   a.Bv = Bv; a.Bt = Bt; a.tiles_per_video = tiles; a.text_rows = (long long)Bt * W;
-  // Two accumulators per CTA pay once the K loops are long (many texts: the sharded global batch); at the per-GPU
-  // batch the loops are too short to amortise the second epilogue.  DVLP_GG_PAIR = 0 / 1 overrides.
+  // Two accumulators per CTA share the streamed operand.  With whole-step stages (k_grad_gemm2) that paid only for
+  // long K loops (>= 128 text tiles, the sharded global batch); with the fine-grained ring it wins from the per-GPU
+  // batch on (measured on B200, both GEMMs: 128 x 128 pairs 72 -> 68 us, 256 x 256 244 -> 173 us, 512 x 512 700 -> 601 us,
+  // 1024 x 1024 2.72 -> 2.39 ms).  DVLP_GG_PAIR = 0 / 1 overrides.
   static const int forced = [] { const char* e = getenv("DVLP_GG_PAIR"); return e ? atoi(e) : -1; }();
-  const bool pair = forced >= 0 ? forced != 0 : tiles >= 128;     // measured: -13 % at 256 tiles, break-even at 64
+  const bool pair = forced >= 0 ? forced != 0 : tiles >= 32;
   // dV' (Bv, R, d): overwritten unless split;  dT' (Bt*W, d): accumulated (the caller zeroes it)
   a.out = (float*)(ws + Lw.dvh) + (size_t)v0 * R * kD; a.accumulate = 0;
   const size_t dv_bytes = (size_t)Bv * R * kD * 4;

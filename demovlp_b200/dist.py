@@ -15,6 +15,8 @@ library and are replaced by an oracle-backed stub in tests/test_dist_cpu.py.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -186,6 +188,7 @@ class ShardedGlobalLocalLoss(nn.Module):
         self.transport = transport          # "p2p": own kernels over peer memory (p2p.py); "nccl": torch.distributed
         self._xchg = None
         self._p2p_failed = False
+        self._side = None                   # stream of the global (CLS) branch, see forward
 
     def global_part(self, text_cls, video_cls, pre=None):
         if pre is None:
@@ -245,8 +248,24 @@ class ShardedGlobalLocalLoss(nn.Module):
             (t_all, v_all, s_all, s_m_all), ticket = xchg.allgather(shards)
         else:
             t_all, v_all, s_all, s_m_all = gather_cat_many(shards, self.group)
-        g = self.global_part(*global_pair, pre=(t_all, v_all))
-        l = self.local_part(local_im, local_s, local_im_m, local_s_m, pre=(s_all, s_m_all), xchg=xchg, ticket=ticket)
+        # The global branch (cosine matrix of the gathered CLS embeddings + NormSoftmax, replicated on every rank) is
+        # independent of the local one until the final add.  Its kernels are small and latency-bound, and so are the
+        # prologue / finalisation / exchange kernels of the local branch, so it runs on a second stream: forward next
+        # to the item prologue, backward (autograd replays a node on the stream of its forward) next to the gradient
+        # finalisation and the reduce-scatter.  Inside a captured step the two streams become parallel graph branches.
+        if t_all.is_cuda and os.environ.get("DVLP_GLOBAL_SIDE_STREAM", "1") != "0":
+            cur = torch.cuda.current_stream(t_all.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(t_all.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                g = self.global_part(*global_pair, pre=(t_all, v_all))
+            l = self.local_part(local_im, local_s, local_im_m, local_s_m, pre=(s_all, s_m_all), xchg=xchg, ticket=ticket)
+            cur.wait_stream(self._side)
+            g.record_stream(cur)
+        else:
+            g = self.global_part(*global_pair, pre=(t_all, v_all))
+            l = self.local_part(local_im, local_s, local_im_m, local_s_m, pre=(s_all, s_m_all), xchg=xchg, ticket=ticket)
         return g + l, g, l
 
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu evidence for the headline kernels at config 3 on one GPU (run under gpurun; reports land in gpurun_out/):
-#   tools/ncu_capture.sh <tag>      e.g. r3
+#   tools/ncu_capture.sh <tag>      e.g. r2b
 # 1. launch list of bench.py (gpu__time_duration per kernel; cold-cache, serialised: compare SHARES)
 # 2. one --set full capture per kernel (third launch of tools/run_c3.py), source-level counters included
 tag=${1:-rX}
