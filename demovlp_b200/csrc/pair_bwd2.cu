@@ -104,11 +104,6 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 __device__ __forceinline__ uint32_t desc_hi32(uint32_t sbo_bytes) {      // 32-byte swizzle
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (6u << 29);
 }
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
   return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }

@@ -85,11 +85,6 @@ struct Args {
 __device__ __forceinline__ uint32_t desc_hi32(uint32_t sbo_bytes) {      // 32-byte swizzle
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (6u << 29);
 }
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
 // Sum over the 32 lanes of the 16 columns held as 8 pairs (pair i = columns 2i, 2i+1): lane l ends with the total
 // of column l & 15.  Lane bit b is paired with column bit b; the columns a lane still holds after a step are those
 // whose bit matches its own, so 16 -> 8 -> 4 -> 2 -> 1 values, then lanes l and l ^ 16 add up.  The adds run as
