@@ -306,12 +306,13 @@ def test_tcgen05_gradients_ragged_text_tiles(shape):
         assert rel_err(y.grad.float().cpu(), sc.grad) < GRAD_TOL
 
 
-@pytest.mark.parametrize("shape", [(3, 80, 512), (5, 48, 509)])
+@pytest.mark.parametrize("shape", [(3, 80, 512), (5, 48, 509), (2, 32, 128), (7, 64, 130)])
 def test_paired_gradient_gemms_odd_video_count(shape):
     """From 32 text tiles on grad_gemm2.cu keeps two accumulators per CTA and contracts dV' in the transposed
     orientation (one MMA over the regions of both videos): an odd video count leaves the last CTA with a single
-    video (N = R instead of 2 R), few videos make the launch split its K loop (atomic partial sums), and 509 texts
-    leave a ragged last text tile.  Gradients against the oracle's autograd (1e-2 relative)."""
+    video (N = R instead of 2 R), few videos make the launch split its K loop (atomic partial sums), and 509 / 130 texts
+    leave a ragged last text tile; every R instantiation of the fine-grained ring is covered.  Gradients against the
+    oracle's autograd (1e-2 relative)."""
     Bv, R, Bt = shape
     b = synth.make_batch(Bt, R, 32, 256, seed=29)
     im = b.im[:Bv].to(torch.bfloat16)
