@@ -117,25 +117,46 @@ __global__ void __launch_bounds__(256) k_sim_bwd_mma(const __nv_bfloat16* __rest
   const uint32_t yb = (uint32_t)__cvta_generic_to_shared(sy);
   const uint32_t whb = (uint32_t)__cvta_generic_to_shared(swh), wlb = (uint32_t)__cvta_generic_to_shared(swl);
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < ny; k0 += 64) {
-    __syncthreads();                       // previous chunk consumed
-    for (int e = threadIdx.x; e < 64 * 32; e += blockDim.x) {
-      const int row = e >> 5, ch = e & 31;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (k0 + row < ny) v = reinterpret_cast<const uint4*>(Y + (size_t)(k0 + row) * kSimD)[ch];
-      *reinterpret_cast<uint4*>(sy + row * kSimLd + ch * 16) = v;
+  // The next 64 rows of the other matrix and their weights travel global -> registers while this chunk's MMAs run
+  // (the loop used to expose one L2 round trip per chunk: 16 of them at 1024 rows).  256 threads: 8 uint4 + 4 weights each.
+  uint4 pre_y[8];
+  float pre_w[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = threadIdx.x + t * 256, row = e >> 5, ch = e & 31;
+      pre_y[t] = make_uint4(0, 0, 0, 0);
+      if (k0 + row < ny) pre_y[t] = reinterpret_cast<const uint4*>(Y + (size_t)(k0 + row) * kSimD)[ch];
     }
-    // weights w[r][c] = d_out(own row i0+r, other row k0+c) * inv_other, split into bf16 hi + lo
-    for (int e = threadIdx.x; e < 16 * 64; e += blockDim.x) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = threadIdx.x + t * 256;
       const int r = side_b ? (e & 15) : (e >> 6), c = side_b ? (e >> 4) : (e & 63);
       const int i = i0 + r, j = k0 + c;
-      float w = 0.f;
-      if (i < nx && j < ny) w = (side_b ? d_out[(size_t)j * M + i] : d_out[(size_t)i * M + j]) * iy[j];
+      pre_w[t] = 0.f;
+      if (i < nx && j < ny) pre_w[t] = (side_b ? d_out[(size_t)j * M + i] : d_out[(size_t)i * M + j]) * iy[j];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < ny; k0 += 64) {
+    __syncthreads();                       // previous chunk consumed
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = threadIdx.x + t * 256, row = e >> 5, ch = e & 31;
+      *reinterpret_cast<uint4*>(sy + row * kSimLd + ch * 16) = pre_y[t];
+    }
+    // weights w[r][c] = d_out(own row i0+r, other row k0+c) * inv_other, split into bf16 hi + lo
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = threadIdx.x + t * 256;
+      const int r = side_b ? (e & 15) : (e >> 6), c = side_b ? (e >> 4) : (e & 63);
+      const float w = pre_w[t];
       const __nv_bfloat16 hi = __float2bfloat16(w);
       const __nv_bfloat16 lo = __float2bfloat16(w - __bfloat162float(hi));
       *reinterpret_cast<__nv_bfloat16*>(swh + r * kLdW + c * 2) = hi;
       *reinterpret_cast<__nv_bfloat16*>(swl + r * kLdW + c * 2) = lo;
     }
+    if (k0 + 64 < ny) fetch(k0 + 64);
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 64; kk += 16) {
