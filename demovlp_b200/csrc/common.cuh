@@ -100,6 +100,16 @@ __device__ __forceinline__ float gt_mask(float a, float b) {
 }
 __device__ __forceinline__ float2 gt_mask2(float2 a, float2 b) { return make_float2(gt_mask(a.x, b.x), gt_mask(a.y, b.y)); }
 
+// 1 / (sqrt(x) + eps) (the l2norm of model/loss.py:333) on the two MUFU approximations (2 ulp each) instead of the IEEE
+// square root and division with their Newton steps and range branches: in the pair kernels both sit on the per-tile
+// dependency chain of every warp (forward at config 3: -3.4 %)
+__device__ __forceinline__ float inv_norm(float x) {
+  float s, r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s + kEps));
+  return r;
+}
+
 // Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream
 // around the kernels of one slot.  Off by default; costs nothing when off.
 enum ProfSlot { kProfFwd = 0, kProfBwd = 1, kProfPrep = 2, kProfFinal = 3, kProfGG = 4, kProfSlots = 5 };

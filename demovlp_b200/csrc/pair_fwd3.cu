@@ -315,7 +315,7 @@ k_pair_fwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
           }
         }
         const float ssA = colsum(sq);                        // sum over the words of this text, column cl
-        const float nAl = a.lam2 / (sqrtf(ssA) + kEps);      // nA * lambda * log2(e)   (model/loss.py:238,244)
+        const float nAl = a.lam2 * inv_norm(ssA);            // nA * lambda * log2(e)   (model/loss.py:238,244)
         if (lane < 16 && q == q0) s_tab[c * NB + cl] = nAl;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
@@ -339,7 +339,7 @@ k_pair_fwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         const float2 p = s_rowx[gg * kRows + m];
         totB += p.x; totA += p.y;
       }
-      const float nB = 1.f / (sqrtf(totB) + kEps);
+      const float nB = inv_norm(totB);
       const float nBl = nB * a.lam2;
       const float thr1 = a.focal ? totA * a.inv_R : -1.f;     // keep e iff e * R > sum_r e  (model/loss.py:280-282), REAL R
 
