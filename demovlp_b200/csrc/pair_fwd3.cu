@@ -370,11 +370,7 @@ k_pair_fwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         float cos2 = num2_p * rden2;                           // padded regions: num2 == 0 exactly
         if (a.colv && lane < 16 && q == q0)
           a.colv[((size_t)u * TPT + t) * a.Rp + c_p * NB + g * 16 + cl] = make_float4(nA_p, thr2_p, rden2, cos2);
-        cos2 += __shfl_xor_sync(0xffffffffu, cos2, 8);
-        cos2 += __shfl_xor_sync(0xffffffffu, cos2, 4);
-        cos2 += __shfl_xor_sync(0xffffffffu, cos2, 2);
-        cos2 += __shfl_xor_sync(0xffffffffu, cos2, 1);
-        acc_t2i += cos2;
+        acc_t2i += cos2;                                       // per lane (= per column); lanes meet once per unit
       };
       for (int c = 0; c < nch; ++c, ++nS, ++nU) {
         const uint32_t slot = nS & 1, vs = nS % kNVec, us = nU & 1;
@@ -482,6 +478,10 @@ k_pair_fwd3(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         cs = warp_sum(cs);
         if (lane == 0) s_fin[NW + q] = cs;
       }
+      acc_t2i += __shfl_xor_sync(0xffffffffu, acc_t2i, 8);    // the 16 columns of this warp (lanes l, l ^ 16 hold the same)
+      acc_t2i += __shfl_xor_sync(0xffffffffu, acc_t2i, 4);
+      acc_t2i += __shfl_xor_sync(0xffffffffu, acc_t2i, 2);
+      acc_t2i += __shfl_xor_sync(0xffffffffu, acc_t2i, 1);
       if (lane == 0) s_fin[cw] = acc_t2i;
       named_bar_sync(1, 128 * NG);
       if (cw == 0 && lane < TPT) {
