@@ -608,7 +608,7 @@ def run_ours(args):
                     "algorithmic_flops_per_pair": (8 if dom == "bwd_pair" else 6) * rwd,
                     "pairs_per_launch": pairs_rank / kern[dom]["launches_per_step"], "peak_source": pk["source"] + ", burst bf16 (SM clock stays at max)",
                     "frac_of_sustained_peak": a / pk["bf16_sustained"],
-                    "note": "co-bound by fp32 ALU/MUFU issue (softmax / focal / l2-norm work per element), see DESIGN.md",
+                    "note": "measured limiter of the pair kernels: the shared-memory data pipe (LSU wavefronts + MMA operand fetch 83-89 % busy, ncu) and per-warp dependency latency of the fp32 softmax / focal / l2-norm work, see DESIGN.md 5.7",
                     "kernels": kern,
                     "step_algorithmic_tflops": 18 * rwd * pairs_step / world / (dev_ms / args.steps * 1e-3) / 1e12}
         tc = bool(lib.dvlp_rw_tcgen05_supported(R, W, D))
