@@ -121,3 +121,76 @@ def test_peer_memory_transport_matches_nccl():
         assert torch.equal(a["d_gt"], c["d_gt"]) and torch.equal(a["d_gv"], c["d_gv"])
     # every rank got the same loss bits from the rank-ordered scalar sum
     assert outs[0]["p2p"]["loss"].item() == outs[1]["p2p"]["loss"].item()
+
+
+def _worker_world1(rank, world, port, out_dir, b):
+    """The sharded module on a process group of ONE rank: eager step, CUDA-graph replay, and the same step with the
+    global (CLS) branch kept on the caller's stream."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    from demovlp_b200 import dist as D, synth
+    from demovlp_b200.graph import GraphedLossStep
+    sh = synth.make_batch(b, 80, 32, 256, seed=7).to("cuda:0")
+    t = dict(im=sh.im.to(torch.bfloat16), s=sh.s.to(torch.bfloat16), g_text=sh.g_text.clone(), g_vid=sh.g_vid.clone())
+    keys = ("im", "s", "g_text", "g_vid")
+    res = {}
+    for name, side in (("side", "1"), ("inline", "0")):
+        os.environ["DVLP_GLOBAL_SIDE_STREAM"] = side
+        mod = D.ShardedGlobalLocalLoss(focal_type="equal", coef=1.0)
+        fn = lambda x: mod((x["g_text"], x["g_vid"]), x["im"], x["s"], sh.im_mask, sh.s_len, sh.s_mask)
+        x = {k: v.detach().clone().requires_grad_(True) for k, v in t.items()}
+        out = fn(x)
+        out[0].backward()
+        torch.cuda.synchronize()
+        res[name] = dict(losses=torch.stack([o.detach().float().cpu() for o in out]),
+                         **{k: x[k].grad.float().cpu() for k in keys})
+        if side == "1":
+            gs = GraphedLossStep(fn, t, keys, warmup=2)
+            for _ in range(3):
+                gs.replay()
+            torch.cuda.synchronize()
+            res["graph"] = dict(losses=gs.losses.float().cpu(), **{k: gs.grads[k].float().cpu() for k in keys})
+    torch.save(res, os.path.join(out_dir, "rank0.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_module_on_one_rank_side_stream_and_graph():
+    """Runs on ONE GPU (the driver's box): ShardedGlobalLocalLoss over a world of one rank must equal GlobalLocalLoss,
+    with the global branch on its second stream (default), inline, and inside a captured whole-step graph, where the
+    two streams become parallel branches."""
+    import torch.multiprocessing as mp
+    from demovlp_b200 import loss as L, synth
+    from tests.util import rel_err
+    b = 32
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker_world1, args=(1, port, td, b), nprocs=1, join=True)
+        res = torch.load(os.path.join(td, "rank0.pt"))
+    full = synth.make_batch(b, 80, 32, 256, seed=7).to("cuda:0")
+    im = full.im.to(torch.bfloat16).requires_grad_(True)
+    s = full.s.to(torch.bfloat16).requires_grad_(True)
+    gt = full.g_text.clone().requires_grad_(True)
+    gv = full.g_vid.clone().requires_grad_(True)
+    out = L.GlobalLocalLoss(focal_type="equal", coef=1.0)(L.sim_matrix(gt, gv), im, s, full.im_mask, full.s_len, full.s_mask)
+    out[0].backward()
+    want = dict(losses=torch.stack([o.detach().float().cpu() for o in out]), im=im.grad.float().cpu(),
+                s=s.grad.float().cpu(), g_text=gt.grad.float().cpu(), g_vid=gv.grad.float().cpu())
+    for name in ("side", "inline", "graph"):
+        got = res[name]
+        assert (got["losses"] - want["losses"]).abs().max() < 1e-4 * max(1.0, float(want["losses"].abs().max())), name
+        for k in ("im", "s"):
+            assert rel_err(got[k], want[k]) < 1e-2, (name, k)
+        for k in ("g_text", "g_vid"):
+            assert rel_err(got[k], want[k]) < 1e-4, (name, k)
+    # the stream placement must not change a bit of the deterministic parts
+    assert torch.equal(res["side"]["losses"], res["inline"]["losses"])
+    assert torch.equal(res["side"]["g_text"], res["inline"]["g_text"])
+    assert torch.equal(res["graph"]["losses"], res["side"]["losses"])
